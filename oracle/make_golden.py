@@ -1,0 +1,115 @@
+"""
+TEST INFRASTRUCTURE ONLY -- regenerate ``tests/golden/*.npz`` by running the
+UNMODIFIED reference (``/root/reference/fastbox``) through ``ref_loader``.
+
+    python oracle/make_golden.py
+
+The fixtures hold the reference's outputs for the canonical inputs of its own
+tests (seeds 11/14, boxes 16^3 @ 100 Mpc, cuboid (1e2,2e2,1e3), 32^3 @ 1 Gpc;
+filter of tests/test_box.py:88-90; sigma_nl RSD; Gaussian beam cube).  Inputs
+are re-derived in the tests from the stored seed with NumPy's legacy global
+generator, exactly as the reference draws them (box.py:174-175, 418).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+CASES = [
+    dict(name="n16_cubic", N=16, scale=(1e2, 1e2, 1e2), seed=11, redshift=0.0),
+    dict(name="n16_cuboid", N=16, scale=(1e2, 2e2, 1e3), seed=11, redshift=1.0),
+    dict(name="n32_gpc", N=32, scale=1e3, seed=14, redshift=0.8),
+]
+
+
+def transfer_fn(k_perp, k_par):                      # tests/test_box.py:88-90
+    return (1. - np.exp(-0.5 * (k_par / 0.001) ** 2.)) * np.exp(-0.5 * (k_perp / 0.1) ** 2.)
+
+
+def beam_cube(N):
+    x = np.arange(N) - N / 2.
+    s = 1.5 + 0.05 * np.arange(N)
+    return np.exp(-0.5 * (x[:, None, None] ** 2 + x[None, :, None] ** 2) / s[None, None, :] ** 2)
+
+
+def run_case(c):
+    box_m = ref_loader.load("box")
+    beams_m = ref_loader.load("beams")
+    halos_m = ref_loader.load("halos")
+    tracers_m = ref_loader.load("tracers")
+    N = c["N"]
+    np.random.seed(c["seed"])
+    box = box_m.CosmoBox(cosmo=box_m.default_cosmo, box_scale=c["scale"], nsamp=N,
+                         redshift=c["redshift"], realise_now=False)
+    box.realise_density()
+    out = dict(N=N, seed=c["seed"], redshift=c["redshift"],
+               scale=np.atleast_1d(np.array(c["scale"], dtype=np.float64)),
+               L=np.array([box.Lx, box.Ly, box.Lz]), boxfactor=box.boxfactor,
+               kmin=box.kmin, kmax=box.kmax,
+               delta_x=box.delta_x, delta_k_half=box.delta_k[:N // 2 + 1])
+    for nb in (20, 50):
+        kc, pk, err = box.binned_power_spectrum(nbins=nb)
+        out["pk%d_k" % nb], out["pk%d_p" % nb], out["pk%d_e" % nb] = kc, pk, err
+        bins = np.logspace(np.log10(box.kmin), np.log10(box.kmax), nb)
+        idx = np.digitize(box.k.flatten(), bins)
+        out["pk%d_counts" % nb] = np.bincount(idx, minlength=nb + 1)
+    s1, s2 = box.test_parseval()
+    out["parseval"] = np.array([s1, s2])
+    vk = box.realise_velocity()
+    vz = np.fft.ifftn(vk[2]).real
+    out["vel_z"] = vz
+    out["vel_x"] = np.fft.ifftn(vk[0]).real
+    out["transfer"] = box.apply_transfer_fn(box.delta_k, transfer_fn).real
+    out["transfer_imag_max"] = np.abs(box.apply_transfer_fn(box.delta_k, transfer_fn).imag).max()
+    out["smooth8"] = box.smooth_field(box.delta_k, 8.0).real
+    tr = tracers_m.HITracer(box)
+    bias = tr.bias_HI()
+    out["bias_HI"] = bias
+    out["Tb"] = tr.signal_amplitude()
+    out["lognormal"] = box.lognormal(box.delta_x * bias)
+    out["rsd0"] = box.redshift_space_density(delta_x=out["lognormal"], velocity_z=vz, sigma_nl=0.)
+    np.random.seed(c["seed"] + 100)
+    out["rsd120"] = box.redshift_space_density(delta_x=out["lognormal"], velocity_z=vz, sigma_nl=120.)
+
+    class GaussBeam(beams_m.BeamModel):
+        def beam_cube(self, pol=None):
+            return beam_cube(N)
+    out["beam_conv"] = GaussBeam(box).convolve_fft(out["rsd0"])
+    # mean halo count (everything before the Poisson draw, halos.py:91-113)
+    hd = halos_m.HaloDistribution(box, (1e12, 1e15), 10)
+    real_poisson = np.random.poisson
+    np.random.poisson = lambda lam: lam
+    try:
+        out["halo_mean_ln"] = hd.halo_count_field(box.delta_x, nbar=1e-3, bias=1.2, lognormal=True)
+        out["halo_mean_lin"] = hd.halo_count_field(box.delta_x, nbar=np.linspace(1e-3, 2e-3, N),
+                                                   bias=1.2, lognormal=False)
+    finally:
+        np.random.poisson = real_poisson
+    out["freq"] = box.freq_array()
+    out["pix_x"] = box.pixel_array()[0]
+    out["z_grid"] = box.z
+    import pyccl as ccl
+    out["Hz"] = 100. * box.cosmo['h'] * ccl.h_over_h0(box.cosmo, box.scale_factor)
+    return out
+
+
+def main():
+    warnings.simplefilter("ignore")
+    dest = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(dest, exist_ok=True)
+    for c in CASES:
+        out = run_case(c)
+        path = os.path.join(dest, c["name"] + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024.))
+
+
+if __name__ == "__main__":
+    main()

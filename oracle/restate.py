@@ -1,0 +1,503 @@
+"""
+TEST INFRASTRUCTURE ONLY -- CPU restatement (NumPy, float64) of the FastBox
+field-generation hot path.  Nothing in ``fastbox_b200/`` imports this file; it
+is the *checker* used by ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+
+Every function names the reference lines it restates (paths relative to
+``/root/reference``).  Parity status: PINNED -- ``tests/test_oracle_cpu.py``
+checks each function against (a) the unmodified reference modules loaded by
+``oracle/ref_loader.py`` when ``/root/reference`` is present and (b) the golden
+vectors in ``tests/golden/`` that ``oracle/make_golden.py`` produced by running
+those reference modules.  Exceptions, which the reference itself delegates to
+packages that are neither vendored nor installed (nbodykit) or that cannot be
+reproduced bit-for-bit (``np.random.poisson``): ``pk_multipoles``,
+``cross_power`` and ``poisson_from_uniform`` are *parity unpinned* and say so.
+
+Two flavours are provided where it matters:
+  * ``*_port``  -- follows the reference step by step (full complex128 cube,
+    ``numpy.fft`` c2c, masked per-bin loops).  This is what is timed as the CPU
+    baseline.
+  * lean versions -- half-spectrum / rfft based, same float64 arithmetic to
+    ~1e-15, usable at 512^3..1024^3 where the port does not fit in RAM.
+"""
+import numpy as np
+
+TWO_PI = 2.0 * np.pi
+
+
+# --------------------------------------------------------------------------
+# Grid and wavenumbers                      fastbox/box.py:76-101, 110-127
+# --------------------------------------------------------------------------
+def box_lengths(box_scale, nsamp):
+    """(Lx, Ly, Lz) exactly as box.py:76-89 derives them from linspace ends."""
+    if isinstance(box_scale, tuple):
+        assert len(box_scale) == 3
+        scales = box_scale
+    else:
+        scales = (box_scale,) * 3
+    out = []
+    for s in scales:
+        g = np.linspace(-0.5 * s, 0.5 * s, nsamp)
+        out.append(g[-1] - g[0])
+    return tuple(out)
+
+
+def grid_coords(scale, nsamp):
+    return np.linspace(-0.5 * scale, 0.5 * scale, nsamp)        # box.py:79-88
+
+
+def boxfactor(N, Lx, Ly, Lz):
+    return (N ** 6.) / (Lx * Ly * Lz)                            # box.py:94
+
+
+def kmin_kmax(N, Lx, Ly, Lz):
+    kmin = 2. * np.pi / np.max([Lx, Ly, Lz])                     # box.py:100
+    kmax = 2. * np.pi * np.sqrt(3.) * N / np.min([Lx, Ly, Lz])   # box.py:101
+    return kmin, kmax
+
+
+def mode_numbers(N):
+    """Signed integer mode numbers, box.py:119 ((N*fftfreq).astype('i'))."""
+    return (N * np.fft.fftfreq(N, 1.)).astype("i")
+
+
+def k_grid(N, Lx, Ly, Lz):
+    """|k| on the full N^3 grid, same operation order as box.py:125-127."""
+    m = mode_numbers(N).astype(np.float64)
+    Kx = m[:, None, None]
+    Ky = m[None, :, None]
+    Kz = m[None, None, :]
+    return TWO_PI * np.sqrt((Kx / Lx) ** 2. + (Ky / Ly) ** 2. + (Kz / Lz) ** 2.)
+
+
+def kperp_kpar(N, Lx, Ly, Lz):
+    """box.py:374-375 (broadcastable shapes instead of N^3 arrays)."""
+    m = mode_numbers(N).astype(np.float64)
+    kperp = TWO_PI * np.sqrt((m[:, None, None] / Lx) ** 2. + (m[None, :, None] / Ly) ** 2.)
+    kpar = TWO_PI * m[None, None, :] / Lz
+    return kperp, kpar
+
+
+# --------------------------------------------------------------------------
+# realise_density                                   fastbox/box.py:130-194
+# --------------------------------------------------------------------------
+def realise_density_port(re, im, pk_of_k, N, Lx, Ly, Lz):
+    """
+    Step-by-step port.  ``pk_of_k(kflat)`` plays CCL's role (box.py:161-165).
+    Returns (delta_x float64 N^3, delta_k complex128 N^3 = fftn(delta_x)).
+    """
+    k = k_grid(N, Lx, Ly, Lz)
+    pk = np.reshape(pk_of_k(k.flatten()), k.shape)
+    pk = np.nan_to_num(pk)                                       # box.py:167
+    pk = pk * boxfactor(N, Lx, Ly, Lz)                           # box.py:171
+    noise_k = (re + 1j * im) * np.sqrt(pk)                       # box.py:176
+    delta_x = np.fft.ifftn(noise_k).real                         # box.py:187
+    delta_k = np.fft.fftn(delta_x)                               # box.py:193
+    return delta_x, delta_k
+
+
+def hermitian_half_from_noise(re, im, amp):
+    """
+    H(k) = amp(k) * 1/2 [ W(k) + conj W(-k) ],  W = re + i im, on the planes
+    kx in [0, N/2] (axis 0 halved).  Identity behind box.py:176-193:
+    fftn(Re ifftn(W*amp)) = H when amp(k)=amp(-k).
+    ``amp`` must broadcast against (N/2+1, N, N).
+    """
+    N = re.shape[0]
+    h = N // 2 + 1
+
+    def mirror(a):                     # a[(-i)%N, (-j)%N, (-l)%N] restricted to i<=N/2
+        ai = np.concatenate([a[:1], a[:0:-1]], axis=0)[:h]        # (-i)%N for i=0..N/2
+        ai = np.concatenate([ai[:, :1], ai[:, :0:-1]], axis=1)
+        ai = np.concatenate([ai[:, :, :1], ai[:, :, :0:-1]], axis=2)
+        return ai
+    hr = 0.5 * (re[:h] + mirror(re))
+    hi = 0.5 * (im[:h] - mirror(im))
+    return (hr + 1j * hi) * amp
+
+
+def irfft3_axis0(half):
+    """Inverse of fftn for a real field given planes kx in [0, N/2] (numpy 1/N^3 norm)."""
+    N = half.shape[1]
+    import scipy.fft
+    return scipy.fft.irfftn(half, s=(N, N, N), axes=(1, 2, 0), workers=-1)
+
+
+def rfft3_axis0(field):
+    import scipy.fft
+    return scipy.fft.rfftn(field, axes=(1, 2, 0), workers=-1)
+
+
+def expand_half_axis0(half):
+    """Full N^3 spectrum of a real field from its kx in [0, N/2] planes."""
+    N = half.shape[1]
+    full = np.empty((N, N, N), dtype=half.dtype)
+    h = N // 2 + 1
+    full[:h] = half
+    rest = half[1:N - h + 1]                                   # kx = 1 .. N/2-1
+    m = np.conj(rest[::-1])                                    # kx = N-1 ... -> ordering N/2+1..N-1
+    m = np.concatenate([m[:, :1], m[:, :0:-1]], axis=1)
+    m = np.concatenate([m[:, :, :1], m[:, :, :0:-1]], axis=2)
+    full[h:] = m
+    return full
+
+
+def sqrt_pk_half(pk_of_k, N, Lx, Ly, Lz):
+    """sqrt(P(k) * boxfactor) on the kx in [0,N/2] half grid (box.py:161-171)."""
+    m = mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    k = TWO_PI * np.sqrt((m[:h, None, None] / Lx) ** 2. + (m[None, :, None] / Ly) ** 2.
+                         + (m[None, None, :] / Lz) ** 2.)
+    pk = np.nan_to_num(np.reshape(pk_of_k(k.ravel()), k.shape))
+    return np.sqrt(pk * boxfactor(N, Lx, Ly, Lz))
+
+
+def realise_density_lean(re, im, pk_of_k, N, Lx, Ly, Lz):
+    """Half-spectrum equivalent of ``realise_density_port`` (agrees to ~1e-15)."""
+    amp = sqrt_pk_half(pk_of_k, N, Lx, Ly, Lz)
+    half = hermitian_half_from_noise(re, im, amp)
+    return irfft3_axis0(half), half
+
+
+# --------------------------------------------------------------------------
+# realise_velocity / realise_potential              fastbox/box.py:197-353
+# --------------------------------------------------------------------------
+def velocity_k_port(delta_k, N, Lx, Ly, Lz, fac):
+    """box.py:251-285.  ``fac`` = 100 h E(a) f(a) a (box.py:280-281)."""
+    m = mode_numbers(N).astype(np.float64)
+    Kx, Ky, Kz = m[:, None, None], m[None, :, None], m[None, None, :]
+    k2 = k_grid(N, Lx, Ly, Lz) ** 2.
+    with np.errstate(divide="ignore", invalid="ignore"):
+        comps = [np.nan_to_num(1.j * delta_k * K * (TWO_PI / L) / k2)
+                 for K, L in ((Kx, Lx), (Ky, Ly), (Kz, Lz))]
+    if N % 2 == 0:                                               # box.py:268-274
+        comps[0][N // 2, :, :] = 0.
+        comps[1][:, N // 2, :] = 0.
+        comps[2][:, :, N // 2] = 0.
+    else:
+        raise NameError("reference fails for odd N (box.py:268-274)")
+    return tuple(c * fac for c in comps)
+
+
+def potential_k_port(delta_k, N, Lx, Ly, Lz):
+    """box.py:347-348 (the prefactor computed at :343-345 is never applied)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        phi = delta_k / k_grid(N, Lx, Ly, Lz) ** 2.
+    phi[0, 0, 0] = 0.
+    return phi
+
+
+# --------------------------------------------------------------------------
+# apply_transfer_fn / smooth_field             fastbox/box.py:356-381,615-655
+# --------------------------------------------------------------------------
+def apply_transfer_fn_port(field_k, transfer_fn, N, Lx, Ly, Lz):
+    kperp, kpar = kperp_kpar(N, Lx, Ly, Lz)
+    kperp = np.broadcast_to(kperp, (N, N, N))
+    kpar = np.broadcast_to(kpar, (N, N, N))
+    dk = np.nan_to_num(field_k * transfer_fn(kperp, kpar))       # box.py:378-379
+    return np.fft.ifftn(dk)                                      # box.py:380 (complex)
+
+
+def tophat_window(k, R):
+    """box.py:631-633."""
+    x = k * R
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (3. / x ** 3.) * (np.sin(x) - x * np.cos(x))
+
+
+def smooth_field_port(field_k, R, h, N, Lx, Ly, Lz):
+    dk = np.nan_to_num(field_k * tophat_window(k_grid(N, Lx, Ly, Lz), R / h))   # box.py:652-653
+    return np.fft.ifftn(dk)
+
+
+# --------------------------------------------------------------------------
+# lognormal                                         fastbox/box.py:441-460
+# --------------------------------------------------------------------------
+def lognormal(delta_x):
+    e = np.exp(delta_x)
+    return e / np.mean(e) - 1.
+
+
+# --------------------------------------------------------------------------
+# binned_power_spectrum                             fastbox/box.py:696-768
+# --------------------------------------------------------------------------
+def pk_bin_edges(N, Lx, Ly, Lz, nbins=20, kbins=None):
+    if kbins is not None:
+        return np.asarray(kbins, dtype=np.float64)
+    kmin, kmax = kmin_kmax(N, Lx, Ly, Lz)
+    return np.logspace(np.log10(kmin), np.log10(kmax), nbins)    # box.py:749
+
+
+def bin_centres(bins):
+    full = [0.0] + list(bins)                                    # box.py:750-751
+    return np.array([0.5 * (full[j + 1] + full[j]) for j in range(len(bins))])
+
+
+def digitize_modes(N, Lx, Ly, Lz, bins):
+    """Integer bin index of every mode of the full grid (box.py:758)."""
+    return np.digitize(k_grid(N, Lx, Ly, Lz).flatten(), bins)
+
+
+def binned_power_spectrum_port(delta_k, N, Lx, Ly, Lz, nbins=20, kbins=None,
+                               return_raw=False):
+    """box.py:741-768 verbatim in structure: per-bin masked mean / std."""
+    pk = (delta_k * np.conj(delta_k)).real / boxfactor(N, Lx, Ly, Lz)
+    bins = pk_bin_edges(N, Lx, Ly, Lz, nbins, kbins)
+    cent = bin_centres(bins)
+    idxs = digitize_modes(N, Lx, Ly, Lz, bins)
+    flat = pk.flatten()
+    vals = np.zeros(bins.size)
+    err = np.zeros(bins.size)
+    counts = np.zeros(bins.size, dtype=np.int64)
+    with np.errstate(all="ignore"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(bins.size):
+                sel = flat[idxs == i]
+                counts[i] = sel.size
+                vals[i] = np.mean(sel)
+                err[i] = np.std(sel) / np.sqrt(sel.size)
+    if return_raw:
+        return cent[1:], vals[1:], err[1:], counts, idxs
+    return cent[1:], vals[1:], err[1:]
+
+
+def pk_moments(power, idxs, nb, weights=None):
+    """(count, sum w p, sum w p^2) for bin indices 0..nb (index nb = overflow)."""
+    w = np.ones_like(power) if weights is None else weights
+    cnt = np.bincount(idxs, weights=w, minlength=nb + 1)
+    s1 = np.bincount(idxs, weights=w * power, minlength=nb + 1)
+    s2 = np.bincount(idxs, weights=w * power * power, minlength=nb + 1)
+    return cnt, s1, s2
+
+
+def half_weights(N):
+    """Multiplicity of each kx in [0,N/2] plane in the full spectrum."""
+    w = np.full(N // 2 + 1, 2.0)
+    w[0] = 1.0
+    if N % 2 == 0:
+        w[-1] = 1.0
+    return w
+
+
+def digitize_half(N, Lx, Ly, Lz, bins):
+    m = mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    k = TWO_PI * np.sqrt((m[:h, None, None] / Lx) ** 2. + (m[None, :, None] / Ly) ** 2.
+                         + (m[None, None, :] / Lz) ** 2.)
+    return np.digitize(k.ravel(), bins).reshape(k.shape)
+
+
+def binned_power_spectrum_lean(half_a, N, Lx, Ly, Lz, nbins=20, kbins=None, half_b=None):
+    """
+    Same estimator from kx in [0,N/2] planes with multiplicity weights
+    (reproduces the port's mean *and* stddev to ~3e-15).  With ``half_b`` the
+    cross spectrum Re[a conj b] is binned instead (PARITY UNPINNED: the
+    reference delegates cross-power to nbodykit, example_halos.py:52-53).
+    """
+    bins = pk_bin_edges(N, Lx, Ly, Lz, nbins, kbins)
+    idx = digitize_half(N, Lx, Ly, Lz, bins)
+    other = half_a if half_b is None else half_b
+    power = (half_a * np.conj(other)).real / boxfactor(N, Lx, Ly, Lz)
+    w = np.broadcast_to(half_weights(N)[:, None, None], power.shape)
+    cnt, s1, s2 = pk_moments(power.ravel(), idx.ravel(), bins.size, w.ravel())
+    with np.errstate(all="ignore"):
+        mean = s1 / cnt
+        var = np.maximum(s2 / cnt - mean * mean, 0.0)
+        err = np.sqrt(var) / np.sqrt(cnt)
+    cent = bin_centres(bins)
+    return cent[1:], mean[1:bins.size], err[1:bins.size], cnt.astype(np.int64)
+
+
+def pk_multipoles(half, N, Lx, Ly, Lz, nbins=20, kbins=None, ells=(0, 2, 4)):
+    """
+    PARITY UNPINNED (reference uses nbodykit FFTPower, example_box.py:48-52).
+    P_l(k) = (2l+1) < |d_k|^2 L_l(mu) >_bin / boxfactor, mu = k_z/|k|, LOS = z,
+    same bins / weights as ``binned_power_spectrum_lean``.
+    """
+    bins = pk_bin_edges(N, Lx, Ly, Lz, nbins, kbins)
+    idx = digitize_half(N, Lx, Ly, Lz, bins)
+    m = mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    kz = TWO_PI * m[None, None, :] / Lz
+    k = TWO_PI * np.sqrt((m[:h, None, None] / Lx) ** 2. + (m[None, :, None] / Ly) ** 2.
+                         + (m[None, None, :] / Lz) ** 2.)
+    with np.errstate(all="ignore"):
+        mu = np.where(k > 0, kz / k, 0.0)
+    power = (half * np.conj(half)).real / boxfactor(N, Lx, Ly, Lz)
+    w = np.broadcast_to(half_weights(N)[:, None, None], power.shape)
+    out = {}
+    cnt = np.bincount(idx.ravel(), weights=w.ravel(), minlength=bins.size + 1)
+    for ell in ells:
+        if ell == 0:
+            leg = np.ones_like(mu)
+        elif ell == 2:
+            leg = 0.5 * (3 * mu ** 2 - 1)
+        elif ell == 4:
+            leg = (35 * mu ** 4 - 30 * mu ** 2 + 3) / 8.0
+        else:
+            raise ValueError(ell)
+        s = np.bincount(idx.ravel(), weights=(w * power * leg).ravel(), minlength=bins.size + 1)
+        with np.errstate(all="ignore"):
+            out[ell] = (2 * ell + 1) * (s / cnt)[1:bins.size]
+    return bin_centres(bins)[1:], out
+
+
+# --------------------------------------------------------------------------
+# redshift_space_density                            fastbox/box.py:384-438
+#   scipy griddata 1-D linear == argsort + interp1d(linear, fill_value)
+#   (scipy/interpolate/_ndgriddata.py:315-330, _interpolate.py:491-518,592-593)
+# --------------------------------------------------------------------------
+def rsd_remap_line(z, dens, vel_total, Hz):
+    s = z - vel_total / Hz                                        # box.py:422
+    zmin = np.min(z)
+    length = np.max(z) - zmin
+    s = (s - zmin) % length + zmin                                # box.py:425-426
+    fill = 0.5 * (dens[0] + dens[-1])                             # box.py:429
+    order = np.argsort(s)
+    xs = s[order]
+    ys = dens[order]
+    hi = np.searchsorted(xs, z).clip(1, xs.size - 1)
+    lo = hi - 1
+    with np.errstate(all="ignore"):
+        slope = (ys[hi] - ys[lo]) / (xs[hi] - xs[lo])
+        val = slope * (z - xs[lo]) + ys[lo]
+    out = np.where((z < xs[0]) | (z > xs[-1]), fill, val)
+    return out
+
+
+def redshift_space_density(delta_x, velocity_z, z, Hz, vel_nl=None):
+    """vel_nl: optional (N,N,N) array = sigma_nl * N(0,1) drawn line by line (box.py:418)."""
+    out = np.empty_like(delta_x)
+    for i in range(delta_x.shape[0]):
+        for j in range(delta_x.shape[1]):
+            v = velocity_z[i, j, :] + (0. if vel_nl is None else vel_nl[i, j, :])
+            out[i, j, :] = rsd_remap_line(z, delta_x[i, j, :], v, Hz)
+    return out
+
+
+# --------------------------------------------------------------------------
+# BeamModel.convolve_fft                           fastbox/beams.py:63-87
+#   scipy.signal.fftconvolve(beam, field, 'same', axes=[0,1]) = zero-padded
+#   linear convolution, cropped to the first argument's frame
+#   (scipy/signal/_signaltools.py: _centered)
+# --------------------------------------------------------------------------
+def convolve_fft(beam, field):
+    N = beam.shape[0]
+    P = 2 * N                              # >= 2N-1 (next_fast_len(2N-1)=2N for N=2^m)
+    fb = np.fft.rfft2(beam, s=(P, P), axes=(0, 1))
+    ff = np.fft.rfft2(field, s=(P, P), axes=(0, 1))
+    full = np.fft.irfft2(fb * ff, s=(P, P), axes=(0, 1))
+    st = (N - 1) // 2
+    sm = full[st:st + N, st:st + N, :]
+    norm = np.sum(beam.reshape(-1, beam.shape[-1]), axis=0)       # beams.py:81
+    return sm / norm[np.newaxis, np.newaxis, :]                   # beams.py:87
+
+
+# --------------------------------------------------------------------------
+# HaloDistribution.halo_count_field                fastbox/halos.py:91-117
+# --------------------------------------------------------------------------
+def halo_mean_count(delta_x, nbar, bias, Lx, Ly, Lz, lognormal_tf=False):
+    """Expected count per voxel (everything in halos.py:91-113 before the Poisson draw)."""
+    N = delta_x.shape[0]
+    nbar = np.atleast_1d(nbar)
+    bias = np.atleast_1d(bias)
+    if nbar.ndim == 1:
+        nbar = nbar[np.newaxis, np.newaxis, :]
+    if bias.ndim == 1:
+        bias = bias[np.newaxis, np.newaxis, :]
+    vol = Lx * Ly * Lz / N ** 3.
+    dh = bias * delta_x
+    if lognormal_tf:
+        dh = np.exp(dh)
+        dh = dh / np.mean(dh)
+        dh = dh - 1.
+    mean = vol * nbar * (1. + dh)
+    if not lognormal_tf:
+        mean = np.where(mean < 0., 0., mean)
+    return np.nan_to_num(mean)
+
+
+def _exp_neg(lam):
+    """exp(-lam) from IEEE + * / only (shared with include/fb_poisson.h: bit-identical)."""
+    lam = np.asarray(lam, dtype=np.float64)
+    n = np.floor(lam * 1.4426950408889634 + 0.5)
+    r = (lam - n * 0.693147180369123816490e+00) - n * 1.90821492927058770002e-10
+    r = -r
+    # exp(r), |r| <= 0.35: Taylor to degree 13 in Horner form
+    p = np.full_like(r, 1.0 / 6227020800.0)
+    for c in (1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+              1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0,
+              1.0 / 6.0, 0.5, 1.0, 1.0):
+        p = p * r + c
+    return np.ldexp(p, (-n).astype(np.int64))
+
+
+def poisson_from_uniform(lam, u, kmax=100000):
+    """
+    PARITY UNPINNED w.r.t. ``np.random.poisson`` (halos.py:116; legacy MT19937
+    stream consumes a variable number of uniforms per sample).  Definition
+    shared bit-for-bit with the CUDA kernel: inversion by sequential search
+        p0 = exp(-lam); count = #{ k : u > sum_{j<=k} p_j },  p_k = p_{k-1} lam / k
+    in float64 using only + * / (no FMA contraction).  lam must be < 700.
+    """
+    lam = np.asarray(lam, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    p = _exp_neg(lam)
+    cdf = p.copy()
+    k = np.zeros(lam.shape, dtype=np.int64)
+    active = u > cdf
+    it = 0
+    while np.any(active) and it < kmax:
+        it += 1
+        k = np.where(active, k + 1, k)
+        p = np.where(active, p * lam / k.clip(1), p)
+        cdf = np.where(active, cdf + p, cdf)
+        active = active & (u > cdf) & (p > 0.0)
+    return k
+
+
+# --------------------------------------------------------------------------
+# Counter-based white noise (no reference equivalent: the reference draws
+# from NumPy's global MT19937, box.py:174-175).  Philox4x32-10 keyed by
+# (seed, global cell index) + Box-Muller; used for throughput / multi-GPU runs.
+# --------------------------------------------------------------------------
+_PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PH_W0, _PH_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+
+
+def philox4x32(ctr, key):
+    """ctr: (...,4) uint32, key: (2,) uint32 -> (...,4) uint32; 10 rounds."""
+    c = [ctr[..., i].astype(np.uint32) for i in range(4)]
+    k0, k1 = np.uint32(key[0]), np.uint32(key[1])
+    mask = np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = _PH_M0 * c[0].astype(np.uint64)
+            p1 = _PH_M1 * c[2].astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & mask).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & mask).astype(np.uint32)
+            c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+            k0 = np.uint32((int(k0) + int(_PH_W0)) & 0xFFFFFFFF)
+            k1 = np.uint32((int(k1) + int(_PH_W1)) & 0xFFFFFFFF)
+    return np.stack(c, axis=-1)
+
+
+def philox_normals(seed, index):
+    """
+    Two N(0,1) per cell: (re, im) of the white noise W at global linear cell
+    ``index`` (uint64 array).  u1 = (x0 + 0.5) 2^-32, u2 = (x1 + 0.5) 2^-32,
+    r = sqrt(-2 ln u1), re = r cos(2 pi u2), im = r sin(2 pi u2).
+    """
+    index = np.asarray(index, dtype=np.uint64)
+    ctr = np.zeros(index.shape + (4,), dtype=np.uint32)
+    ctr[..., 0] = (index & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[..., 1] = (index >> np.uint64(32)).astype(np.uint32)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    x = philox4x32(ctr, key)
+    u1 = (x[..., 0].astype(np.float64) + 0.5) * 2.0 ** -32
+    u2 = (x[..., 1].astype(np.float64) + 0.5) * 2.0 ** -32
+    r = np.sqrt(-2.0 * np.log(u1))
+    return r * np.cos(TWO_PI * u2), r * np.sin(TWO_PI * u2)
