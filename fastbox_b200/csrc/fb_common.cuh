@@ -1,0 +1,172 @@
+// fb_common.cuh -- plan object, error handling, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/fastbox_b200.h"
+#include "fb_fft.cuh"
+
+namespace fb {
+
+#define FB_MAX_EDGES 128
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define FB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            fb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return -2;                                                                             \
+        }                                                                                          \
+    } while (0)
+
+#define FB_CHECK(cond, ...)          \
+    do {                             \
+        if (!(cond)) {               \
+            fb::set_error(__VA_ARGS__); \
+            return -1;               \
+        }                            \
+    } while (0)
+
+#define FB_LAUNCH_CHECK()                                                                       \
+    do {                                                                                        \
+        fb::g_launches.fetch_add(1);                                                            \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            fb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return -3;                                                                          \
+        }                                                                                       \
+    } while (0)
+
+// Everything a first/last pass needs to know about k-space.
+struct KSpace {
+    int N;
+    int a0;                 // global kx index of local plane 0 (slab decomposition)
+    float inv_lx2, inv_ly2, inv_lz2;     // 1/L^2
+    float two_pi_over_lx, two_pi_over_ly, two_pi_over_lz;
+    // sqrt(P) table
+    const float* sqrtp;
+    int sqrtp_mode;         // 0 none, 1 integer |m|^2 LUT, 2 log2(s) table
+    int sqrtp_n;
+    float log2s0, inv_dlog2s;
+    // filter
+    const float* tperp;     // [(N/2+1)*N]
+    const float* tpar;      // [N]
+    const float* tdense;    // [(N/2+1)*N*N]
+    // P(k) binning
+    const double* ax;       // (m/Lx)^2 per axis index, float64, bitwise as NumPy
+    const double* ay;
+    const double* az;
+    const double* thr;      // thresholds on s
+    int nedges;
+    double inv_boxfactor;
+};
+
+struct PkDev {              // device histogram, nb+1 entries each
+    unsigned long long* count;
+    double* sum1;
+    double* sum2;
+    double* l2;
+    double* l4;
+};
+
+}  // namespace fb
+
+struct fb_plan {
+    int N;
+    double Lx, Ly, Lz;
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    // slab
+    int a0, na, y0, ny;
+    // tables
+    float2* tw;
+    double *ax, *ay, *az, *thr;
+    int nedges;
+    float* sqrtp;
+    int sqrtp_mode;
+    long sqrtp_n;
+    double log2s0, dlog2s;
+    float *tperp, *tpar, *tdense;
+    // workspaces
+    float2* work;           // [(na)][N][N] complex
+    size_t work_bytes;
+    void* stage[6];         // host-staging device buffers
+    size_t stage_bytes[6];
+    void* pinned;           // pinned bounce buffer for pageable host memory
+    size_t pinned_bytes;
+    unsigned long long* h_count;
+    double* h_sums;         // 4 arrays of FB_MAX_EDGES+1
+    double* scal;           // device scalars [8]
+    double* scal_host;      // pinned
+    // beam / misc workspaces
+    void* aux;
+    size_t aux_bytes;
+    cudaEvent_t ev[8];
+    float last_ms[8];
+    int n_last;
+    fb::KSpace kspace() const;
+    fb::PkDev pkdev() const;
+};
+
+namespace fb {
+
+int ensure_work(fb_plan* p);
+int ensure_aux(fb_plan* p, size_t bytes);
+// returns device pointer for an input buffer (stages host memory into slot)
+int stage_in(fb_plan* p, int slot, const void* ptr, size_t bytes, const void** dev);
+// returns device pointer to write results to; if `ptr` is host memory a staging slot is used
+int stage_out_begin(fb_plan* p, int slot, void* ptr, size_t bytes, void** dev);
+int stage_out_end(fb_plan* p, int slot, void* ptr, size_t bytes);
+bool is_device_ptr(const void* ptr);
+int pk_clear(fb_plan* p);
+int pk_fetch(fb_plan* p, fb_pk_result* out);
+
+__device__ __forceinline__ int mode_number(int i, int N) { return i < N / 2 ? i : i - N; }   // box.py:119
+
+// warp sum of a double
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- Philox4x32-10 (counter = cell index, key = seed) + Box-Muller ----------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+}
+__device__ __forceinline__ float2 philox_normal_pair(uint64_t seed, uint64_t index) {
+    uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    // u in (0,1): (x + 0.5) * 2^-32
+    const float u1 = (float)(c[0] >> 8) * 5.9604644775390625e-08f;                      // exact
+    const float u1lo = ((float)(c[0] & 0xffu) + 0.5f) * 2.3283064365386963e-10f;         // exact
+    const float u = u1 + u1lo;      // fl((x0+0.5)/2^32), > 0
+    const float r = sqrtf(-2.0f * logf(u));
+    float s, co;
+    const float u2 = ((float)c[1] + 0.5f) * 2.3283064365386963e-10f;
+    sincospif(2.0f * u2, &s, &co);
+    return make_float2(r * co, r * s);
+}
+
+}  // namespace fb

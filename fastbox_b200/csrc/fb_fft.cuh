@@ -1,0 +1,209 @@
+// fb_fft.cuh -- register-resident Stockham FFT building blocks (sm_100a).
+//
+// One FFT of length n is computed by T = n/P threads; every thread keeps P
+// complex points in registers.  Element ownership is the same at the input of
+// every stage and at the final output:  thread t holds elements  t + T*q,
+// q = 0..P-1  (register q).  A stage of radix R (R | P) lets each thread do
+// P/R butterflies in registers; between stages the points are exchanged
+// through shared memory (write at the Stockham position j0 + r*Ns, read back
+// at t + T*q).  This replaces numpy.fft / pocketfft used by the reference at
+// fastbox/box.py:187,193,246,337,380,654,736.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fb {
+
+#define FB_NMAX_TW 4096      // master twiddle table length (forward sign), owned by the plan
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// cos(pi*m/16), m = 0..16
+__host__ __device__ constexpr float cos_pi16(int m) {
+    constexpr double C[17] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                              0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                              0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
+                              -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                              -0.92387953251128675613, -0.98078528040323044913, -1.0};
+    return (float)C[m];
+}
+__host__ __device__ constexpr float sin_pi16(int m) {   // sin(pi*m/16) = cos(pi*(8-m)/16), m = 0..16
+    return m <= 8 ? cos_pi16(8 - m) : cos_pi16(m - 8);
+}
+
+// multiply by exp(S * i * pi * M16 / 16), M16 in [0,16), compile-time
+template <int M16, int S>
+__device__ __forceinline__ float2 ctwiddle(float2 a) {
+    if constexpr (M16 == 0) {
+        return a;
+    } else if constexpr (M16 == 8) {          // * (S i)
+        return S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+    } else if constexpr (M16 == 4) {          // * (1 + S i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return S > 0 ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
+    } else if constexpr (M16 == 12) {         // * (-1 + S i)/sqrt2
+        constexpr float h = 0.70710678118654752440f;
+        return S > 0 ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+    } else {
+        constexpr float c = cos_pi16(M16);
+        constexpr float s = (S > 0 ? 1.f : -1.f) * sin_pi16(M16);
+        return make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.x, s, a.y * c));
+    }
+}
+
+// Natural-order in / natural-order out DFT of R points held in registers.
+template <int R, int S>
+struct Dft;
+
+template <int S>
+struct Dft<1, S> {
+    __device__ __forceinline__ static void run(float2 (&)[1]) {}
+};
+template <int S>
+struct Dft<2, S> {
+    __device__ __forceinline__ static void run(float2 (&a)[2]) {
+        float2 t = a[0];
+        a[0] = cadd(t, a[1]);
+        a[1] = csub(t, a[1]);
+    }
+};
+template <int S>
+struct Dft<4, S> {
+    __device__ __forceinline__ static void run(float2 (&a)[4]) {
+        float2 b0 = cadd(a[0], a[2]), b1 = csub(a[0], a[2]);
+        float2 b2 = cadd(a[1], a[3]), b3 = ctwiddle<8, S>(csub(a[1], a[3]));
+        a[0] = cadd(b0, b2);
+        a[2] = csub(b0, b2);
+        a[1] = cadd(b1, b3);
+        a[3] = csub(b1, b3);
+    }
+};
+template <int R, int S>
+struct Dft {
+    __device__ __forceinline__ static void run(float2 (&a)[R]) {
+        constexpr int H = R / 2;
+        float2 e[H], o[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            e[i] = a[2 * i];
+            o[i] = a[2 * i + 1];
+        }
+        Dft<H, S>::run(e);
+        Dft<H, S>::run(o);
+        combine<0>(a, e, o);
+    }
+    template <int K>
+    __device__ __forceinline__ static void combine(float2 (&a)[R], float2 (&e)[R / 2], float2 (&o)[R / 2]) {
+        if constexpr (K < R / 2) {
+            float2 w = ctwiddle<(K * 32) / R, S>(o[K]);
+            a[K] = cadd(e[K], w);
+            a[K + R / 2] = csub(e[K], w);
+            combine<K + 1>(a, e, o);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Shared-memory layouts for the exchange buffer.
+//   RowLayout : one FFT per smem row, padded one float2 every 16 (bank spread
+//               for the stride-R Stockham writes).
+//   ColLayout : CZ FFTs interleaved (element-major); conflict free for CZ>=16.
+// ---------------------------------------------------------------------------
+template <int n>
+struct RowLayout {
+    static constexpr int ROW = n + n / 16;
+    int base;
+    __device__ __forceinline__ int operator()(int i) const { return base + i + (i >> 4); }
+};
+template <int CZ>
+struct ColLayout {
+    int col;
+    __device__ __forceinline__ int operator()(int i) const { return i * CZ + col; }
+};
+
+template <int n, int P, int R, int Ns, int S>
+__device__ __forceinline__ void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
+    constexpr int T = n / P;
+    constexpr int B = P / R;
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+        float2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r] = v[u + r * B];
+        if constexpr (Ns > 1) {
+            const int jm = (t + u * T) & (Ns - 1);
+            constexpr int step = (FB_NMAX_TW / (Ns * R));
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = __ldg(&tw[r * jm * step]);
+                if (S > 0) w.y = -w.y;
+                a[r] = cmul(a[r], w);
+            }
+        }
+        Dft<R, S>::run(a);
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[u + r * B] = a[r];
+    }
+}
+
+// write the outputs of a radix-R stage (previous product Ns) to smem, read back
+// the inputs of the next stage.  Two barriers: the buffer is reused in place.
+template <int n, int P, int R, int Ns, class SL>
+__device__ __forceinline__ void fft_exchange(float2 (&v)[P], int t, float2* sm, const SL& sl, bool trailing_sync) {
+    constexpr int T = n / P;
+    constexpr int B = P / R;
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+        const int j = t + u * T;
+        const int j0 = (j / Ns) * (Ns * R) + (j & (Ns - 1));
+#pragma unroll
+        for (int r = 0; r < R; ++r) sm[sl(j0 + r * Ns)] = v[u + r * B];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < P; ++q) v[q] = sm[sl(t + T * q)];
+    if (trailing_sync) __syncthreads();
+}
+
+// Full length-n transform of the register-resident points.
+template <int n, int P, int R1, int R2, int R3, int S, class SL>
+__device__ __forceinline__ void fft_regs(float2 (&v)[P], int t, float2* sm, const SL& sl,
+                                         const float2* __restrict__ tw) {
+    static_assert(R1 * R2 * R3 == n, "radix product");
+    fft_stage<n, P, R1, 1, S>(v, t, tw);
+    if constexpr (R2 > 1) {
+        fft_exchange<n, P, R1, 1, SL>(v, t, sm, sl, R3 > 1);
+        fft_stage<n, P, R2, R1, S>(v, t, tw);
+    }
+    if constexpr (R3 > 1) {
+        fft_exchange<n, P, R2, R1, SL>(v, t, sm, sl, false);
+        fft_stage<n, P, R3, R1 * R2, S>(v, t, tw);
+    }
+}
+
+// compile-time FFT configuration for each supported length
+template <int n>
+struct FftCfg;
+#define FB_CFG(N_, P_, A_, B_, C_)                                              \
+    template <>                                                                 \
+    struct FftCfg<N_> {                                                         \
+        static constexpr int n = N_, P = P_, R1 = A_, R2 = B_, R3 = C_, T = N_ / P_; \
+    };
+FB_CFG(4, 4, 4, 1, 1)
+FB_CFG(8, 8, 8, 1, 1)
+FB_CFG(16, 16, 16, 1, 1)
+FB_CFG(32, 16, 16, 2, 1)
+FB_CFG(64, 16, 16, 4, 1)
+FB_CFG(128, 16, 16, 8, 1)
+FB_CFG(256, 16, 16, 16, 1)
+FB_CFG(512, 16, 16, 16, 2)
+FB_CFG(1024, 16, 16, 16, 4)
+FB_CFG(2048, 16, 16, 16, 8)
+#undef FB_CFG
+
+}  // namespace fb

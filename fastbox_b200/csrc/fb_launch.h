@@ -1,0 +1,47 @@
+// fb_launch.h -- launcher entry points shared between translation units.
+#pragma once
+#include "fb_passes.cuh"
+
+namespace fb {
+
+int launch_rows_inv_noise(fb_plan* p, const RowsArgs& a);
+int launch_rows_inv_philox(fb_plan* p, const RowsArgs& a);
+int launch_rows_inv_spec(fb_plan* p, const RowsArgs& a);
+int launch_rows_inv_cube(fb_plan* p, const RowsArgs& a);
+int launch_rows_fwd(fb_plan* p, const RowsArgs& a);
+int launch_pk_spectrum(fb_plan* p, const float2* spec, const float2* cross, int nplanes, int full_cube, int flags);
+int launch_cols(fb_plan* p, float2* data, int nplanes, int sign);
+int launch_x_c2r(fb_plan* p, const XArgs& a);
+int launch_x_r2c(fb_plan* p, const XArgs& a);
+
+int env_int(const char* name, int dflt);
+
+#define FB_DISPATCH_N(N_, MACRO)                                 \
+    switch (N_) {                                                \
+        case 8: MACRO(8); break;                                 \
+        case 16: MACRO(16); break;                               \
+        case 32: MACRO(32); break;                               \
+        case 64: MACRO(64); break;                               \
+        case 128: MACRO(128); break;                             \
+        case 256: MACRO(256); break;                             \
+        case 512: MACRO(512); break;                             \
+        case 1024: MACRO(1024); break;                           \
+        case 2048: MACRO(2048); break;                           \
+        default:                                                 \
+            fb::set_error("unsupported grid size N=%d (power of two in [8,2048])", N_); \
+            return -1;                                           \
+    }
+
+template <class Kern>
+inline int set_smem(Kern kern, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
+            return -2;
+        }
+    }
+    return 0;
+}
+
+}  // namespace fb

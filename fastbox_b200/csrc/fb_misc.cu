@@ -1,0 +1,386 @@
+// fb_misc.cu -- streaming kernels around the FFT pipeline: affine / exp / moments,
+// dtype conversion, redshift-space remap (box.py:412-437), halo counts (halos.py:91-117),
+// and a strided-copy probe used to pick tile widths.
+#include "fb_launch.h"
+#include "../../include/fb_poisson.h"
+
+namespace fb {
+
+static inline unsigned grid_for(size_t n, int per_block, int sm_count) {
+    size_t b = (n + per_block - 1) / per_block;
+    const size_t cap = (size_t)sm_count * 16;
+    return (unsigned)(b < cap ? (b ? b : 1) : cap);
+}
+
+__global__ void __launch_bounds__(256) k_affine(float* __restrict__ x, size_t n, float mul, float add) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n4 = n / 4;
+    float4* x4 = reinterpret_cast<float4*>(x);
+    for (; i < n4; i += stride) {
+        float4 v = x4[i];
+        v.x = fmaf(v.x, mul, add);
+        v.y = fmaf(v.y, mul, add);
+        v.z = fmaf(v.z, mul, add);
+        v.w = fmaf(v.w, mul, add);
+        x4[i] = v;
+    }
+    for (size_t j = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        x[j] = fmaf(x[j], mul, add);
+}
+
+__device__ __forceinline__ void block_sum2(double a, double b, double* out) {
+    __shared__ double red[2][32];
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red[0][warp] = a;
+        red[1][warp] = b;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        a = lane < nw ? red[0][lane] : 0.0;
+        b = lane < nw ? red[1][lane] : 0.0;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            atomicAdd(&out[0], a);
+            atomicAdd(&out[1], b);
+        }
+    }
+}
+
+// out = exp(scale*in); sums[0] += sum(out)
+__global__ void __launch_bounds__(256) k_exp_sum(const float* __restrict__ in, float* __restrict__ out, size_t n,
+                                                  float scale, double* sums) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float e = expf(in[i] * scale);
+        out[i] = e;
+        acc += (double)e;
+    }
+    block_sum2(acc, 0.0, sums);
+}
+
+__global__ void __launch_bounds__(256) k_moments(const float* __restrict__ in, size_t n, double* sums) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    double a = 0.0, b = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = (double)in[i];
+        a += v;
+        b += v * v;
+    }
+    block_sum2(a, b, sums);
+}
+
+__global__ void __launch_bounds__(256) k_f64_to_f32(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (float)src[i];
+}
+__global__ void __launch_bounds__(256) k_f32_to_f64(const float* __restrict__ src, double* __restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (double)src[i];
+}
+
+// ---------------------------------------------------------------------------
+// Redshift-space remap, one CTA per line of sight (box.py:412-437).
+//   s = z - (v_z + v_nl)/H ; periodic wrap ; sort (s, delta) ; linear re-grid onto z
+//   (scipy griddata 1-D = argsort + interp1d(linear, fill_value)), coordinates in float64.
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__((N / 2) < 32 ? 32 : (N / 2)) k_rsd_remap(const float* __restrict__ delta,
+                                                                          const float* __restrict__ vel,
+                                                                          const float* __restrict__ vnl,
+                                                                          const double* __restrict__ zgrid,
+                                                                          double Hz, float* __restrict__ out) {
+    __shared__ double key[N];
+    __shared__ float val[N];
+    __shared__ double zz[N];
+    const size_t line = (size_t)blockIdx.x * N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double zmin = zgrid[0], zmax = zgrid[N - 1];       // grid is increasing (linspace, box.py:79-88)
+    const double length = zmax - zmin;
+    for (int l = tid; l < N; l += nt) {
+        const double zl = zgrid[l];
+        zz[l] = zl;
+        double v = (double)vel[line + l];
+        if (vnl) v += (double)vnl[line + l];
+        double s = zl - v / Hz;                                // box.py:422
+        double r = fmod(s - zmin, length);                     // Python float % : sign of divisor
+        if (r != 0.0 && r < 0.0) r += length;
+        key[l] = r + zmin;                                     // box.py:426
+        val[l] = delta[line + l];
+    }
+    __syncthreads();
+    const float fill = 0.5f * (val[0] + val[N - 1]);           // box.py:429 (before sorting)
+    __syncthreads();
+    // bitonic sort, ascending in key
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < N / 2; i += nt) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const bool up = (lo & k) == 0;
+                const double a = key[lo], b = key[hi];
+                if ((a > b) == up) {
+                    key[lo] = b;
+                    key[hi] = a;
+                    const float t = val[lo];
+                    val[lo] = val[hi];
+                    val[hi] = t;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const double x_first = key[0], x_last = key[N - 1];
+    for (int l = tid; l < N; l += nt) {
+        const double x = zz[l];
+        int lo = 0, hi = N;                                   // searchsorted(xs, x, 'left')
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (key[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        int ih = lo < 1 ? 1 : (lo > N - 1 ? N - 1 : lo);
+        const int il = ih - 1;
+        const double xl = key[il], xh = key[ih];
+        const double yl = (double)val[il], yh = (double)val[ih];
+        const double slope = (yh - yl) / (xh - xl);
+        double r = slope * (x - xl) + yl;
+        if (x < x_first || x > x_last) r = (double)fill;
+        out[line + l] = (float)r;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// halo counts: mean count lambda in float64 from the float32 density, then
+// Poisson inversion from the supplied uniform (halos.py:104-117).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_exp_sum_f64(const float* __restrict__ delta, const float* __restrict__ bias,
+                                                      int bias_kind, int N, size_t n, double* sums) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double b = (double)(bias_kind == 0 ? bias[0] : (bias_kind == 1 ? bias[i % N] : bias[i]));
+        acc += exp(b * (double)delta[i]);
+    }
+    block_sum2(acc, 0.0, sums);
+}
+
+__global__ void __launch_bounds__(256) k_halo_counts(const float* __restrict__ delta, const float* __restrict__ nbar,
+                                                      int nbar_kind, const float* __restrict__ bias, int bias_kind,
+                                                      int lognormal, double mean_exp, double voxel_vol,
+                                                      const double* __restrict__ uniforms, int N, size_t n,
+                                                      int32_t* __restrict__ counts, float* __restrict__ mean_out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double b = (double)(bias_kind == 0 ? bias[0] : (bias_kind == 1 ? bias[i % N] : bias[i]));
+        const double nb = (double)(nbar_kind == 0 ? nbar[0] : (nbar_kind == 1 ? nbar[i % N] : nbar[i]));
+        double dh = __dmul_rn(b, (double)delta[i]);                       // halos.py:104
+        if (lognormal) dh = __dadd_rn(__ddiv_rn(exp(dh), mean_exp), -1.0);  // halos.py:106-108
+        double lam = __dmul_rn(__dmul_rn(voxel_vol, nb), __dadd_rn(1.0, dh));   // halos.py:111
+        if (!lognormal && lam < 0.0) lam = 0.0;                           // halos.py:112-113
+        if (lam != lam) lam = 0.0;                                         // nan_to_num, halos.py:116
+        if (mean_out) mean_out[i] = (float)lam;
+        if (counts) counts[i] = fb_poisson_inv(lam, uniforms[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// strided copy probe: tiles of `rows` x `chunk` bytes, rows `row_stride` apart
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_strided_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, int rows,
+                                                       int chunk16, size_t row_stride16, int chunks_per_row,
+                                                       size_t plane_stride16) {
+    const size_t tile = blockIdx.x;
+    const size_t plane = tile / chunks_per_row, ch = tile % chunks_per_row;
+    const size_t base = plane * plane_stride16 + ch * chunk16;
+    const int total = rows * chunk16;
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) v[u] = src[base + (size_t)(i / chunk16) * row_stride16 + (i % chunk16)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) dst[base + (size_t)(i / chunk16) * row_stride16 + (i % chunk16)] = v[u];
+        }
+    }
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_affine(fb_plan* p, float* field, size_t n, float mul, float add) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(is_device_ptr(field), "fb_affine: field must be device memory");
+    k_affine<<<grid_for(n / 4 + 1, 256, p->sm_count), 256, 0, p->stream>>>(field, n, mul, add);
+    FB_LAUNCH_CHECK();
+    return 0;
+}
+
+int fb_exp_sum(fb_plan* p, const float* in, float* out, size_t n, float scale, double* sum_out) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(is_device_ptr(in) && is_device_ptr(out), "fb_exp_sum: buffers must be device memory");
+    FB_CUDA(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
+    k_exp_sum<<<grid_for(n, 256, p->sm_count), 256, 0, p->stream>>>(in, out, n, scale, p->scal);
+    FB_LAUNCH_CHECK();
+    FB_CUDA(cudaMemcpyAsync(p->scal_host, p->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    if (sum_out) *sum_out = p->scal_host[0];
+    return 0;
+}
+
+int fb_field_moments(fb_plan* p, const float* field, size_t n, double* sum, double* sumsq) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const void* d = nullptr;
+    if (stage_in(p, 2, field, n * sizeof(float), &d)) return -2;
+    FB_CUDA(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
+    k_moments<<<grid_for(n, 256, p->sm_count), 256, 0, p->stream>>>((const float*)d, n, p->scal);
+    FB_LAUNCH_CHECK();
+    FB_CUDA(cudaMemcpyAsync(p->scal_host, p->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    if (sum) *sum = p->scal_host[0];
+    if (sumsq) *sumsq = p->scal_host[1];
+    return 0;
+}
+
+int fb_convert_f64_to_f32(fb_plan* p, const double* src, float* dst, size_t n) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(is_device_ptr(dst), "fb_convert_f64_to_f32: dst must be device memory");
+    const void* d = nullptr;
+    if (stage_in(p, 5, src, n * sizeof(double), &d)) return -2;
+    k_f64_to_f32<<<grid_for(n, 256, p->sm_count), 256, 0, p->stream>>>((const double*)d, dst, n);
+    FB_LAUNCH_CHECK();
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int fb_convert_f32_to_f64(fb_plan* p, const float* src, double* dst, size_t n) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(is_device_ptr(src), "fb_convert_f32_to_f64: src must be device memory");
+    void* d = nullptr;
+    if (stage_out_begin(p, 5, dst, n * sizeof(double), &d)) return -2;
+    k_f32_to_f64<<<grid_for(n, 256, p->sm_count), 256, 0, p->stream>>>(src, (double*)d, n);
+    FB_LAUNCH_CHECK();
+    if (stage_out_end(p, 5, dst, n * sizeof(double))) return -2;
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int fb_rsd_remap(fb_plan* p, const float* delta, const float* vel_z, const float* vel_nl, const double* zgrid,
+                 double Hz, float* out) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const int N = p->N;
+    const size_t n3 = (size_t)N * N * N;
+    FB_CHECK(delta && vel_z && zgrid && out, "fb_rsd_remap: NULL buffer");
+    FB_CHECK(Hz > 0, "fb_rsd_remap: Hz must be positive");
+    const void *dd = nullptr, *dv = nullptr, *dn = nullptr;
+    void* dout = nullptr;
+    if (stage_in(p, 0, delta, n3 * sizeof(float), &dd)) return -2;
+    if (stage_in(p, 1, vel_z, n3 * sizeof(float), &dv)) return -2;
+    if (stage_in(p, 4, vel_nl, n3 * sizeof(float), &dn)) return -2;
+    if (stage_out_begin(p, 2, out, n3 * sizeof(float), &dout)) return -2;
+    if (ensure_aux(p, (size_t)N * sizeof(double))) return -2;
+    FB_CUDA(cudaMemcpyAsync(p->aux, zgrid, (size_t)N * sizeof(double), cudaMemcpyDefault, p->stream));
+    const unsigned lines = (unsigned)((size_t)N * N);
+#define FB_RSD(N_)                                                                                         \
+    k_rsd_remap<N_><<<lines, ((N_ / 2) < 32 ? 32 : (N_ / 2)), 0, p->stream>>>(                             \
+        (const float*)dd, (const float*)dv, (const float*)dn, (const double*)p->aux, Hz, (float*)dout)
+    FB_DISPATCH_N(N, FB_RSD);
+#undef FB_RSD
+    FB_LAUNCH_CHECK();
+    if (stage_out_end(p, 2, out, n3 * sizeof(float))) return -2;
+    return 0;
+}
+
+int fb_halo_counts(fb_plan* p, const float* delta, const float* nbar, int nbar_kind, const float* bias, int bias_kind,
+                   int lognormal, double mean_exp, const double* uniforms, int32_t* counts_out, float* mean_out) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const int N = p->N;
+    const size_t n3 = (size_t)N * N * N;
+    FB_CHECK(delta && nbar && bias, "fb_halo_counts: NULL buffer");
+    FB_CHECK(nbar_kind >= 0 && nbar_kind <= 2 && bias_kind >= 0 && bias_kind <= 2, "fb_halo_counts: bad kind");
+    FB_CHECK((counts_out == nullptr) || (uniforms != nullptr), "fb_halo_counts: counts need uniforms");
+    const size_t sz[3] = {1, (size_t)N, n3};
+    const void *dd = nullptr, *dnb = nullptr, *dbi = nullptr, *du = nullptr;
+    void *dc = nullptr, *dm = nullptr;
+    if (stage_in(p, 0, delta, n3 * sizeof(float), &dd)) return -2;
+    if (ensure_aux(p, (sz[nbar_kind] + sz[bias_kind]) * sizeof(float))) return -2;
+    float* a_nb = (float*)p->aux;
+    float* a_bi = a_nb + sz[nbar_kind];
+    if (is_device_ptr(nbar)) dnb = nbar; else {
+        FB_CUDA(cudaMemcpyAsync(a_nb, nbar, sz[nbar_kind] * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        dnb = a_nb;
+    }
+    if (is_device_ptr(bias)) dbi = bias; else {
+        FB_CUDA(cudaMemcpyAsync(a_bi, bias, sz[bias_kind] * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        dbi = a_bi;
+    }
+    if (stage_in(p, 5, uniforms, n3 * sizeof(double), &du)) return -2;
+    if (stage_out_begin(p, 1, counts_out, n3 * sizeof(int32_t), &dc)) return -2;
+    if (stage_out_begin(p, 2, mean_out, n3 * sizeof(float), &dm)) return -2;
+    if (lognormal && !(mean_exp > 0.0)) {
+        FB_CUDA(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
+        k_exp_sum_f64<<<grid_for(n3, 256, p->sm_count), 256, 0, p->stream>>>((const float*)dd, (const float*)dbi,
+                                                                            bias_kind, N, n3, p->scal);
+        FB_LAUNCH_CHECK();
+        FB_CUDA(cudaMemcpyAsync(p->scal_host, p->scal, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        FB_CUDA(cudaStreamSynchronize(p->stream));
+        mean_exp = p->scal_host[0] / (double)n3;
+    }
+    const double vol = p->Lx * p->Ly * p->Lz / pow((double)N, 3.0);        // halos.py:101
+    k_halo_counts<<<grid_for(n3, 256, p->sm_count), 256, 0, p->stream>>>(
+        (const float*)dd, (const float*)dnb, nbar_kind, (const float*)dbi, bias_kind, lognormal, mean_exp, vol,
+        (const double*)du, N, n3, (int32_t*)dc, (float*)dm);
+    FB_LAUNCH_CHECK();
+    if (stage_out_end(p, 1, counts_out, n3 * sizeof(int32_t))) return -2;
+    if (stage_out_end(p, 2, mean_out, n3 * sizeof(float))) return -2;
+    return 0;
+}
+
+int fb_bench_strided_copy(fb_plan* p, size_t total_bytes, int chunk_bytes, int iters, double* gbs) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(chunk_bytes >= 16 && (chunk_bytes % 16) == 0, "chunk must be a multiple of 16 bytes");
+    const int rows = 1024;
+    const size_t row_bytes = 8192;                       // one z row of a 1024^3 complex64 cube
+    const size_t plane_bytes = rows * row_bytes;
+    const size_t planes = total_bytes / plane_bytes;
+    FB_CHECK(planes >= 1, "total_bytes too small");
+    const int chunks_per_row = (int)(row_bytes / chunk_bytes);
+    void *src = nullptr, *dst = nullptr;
+    FB_CUDA(cudaMalloc(&src, planes * plane_bytes));
+    FB_CUDA(cudaMalloc(&dst, planes * plane_bytes));
+    FB_CUDA(cudaMemsetAsync(src, 1, planes * plane_bytes, p->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const unsigned grid = (unsigned)(planes * chunks_per_row);
+    for (int it = 0; it < iters + 1; ++it) {
+        if (it == 1) cudaEventRecord(e0, p->stream);
+        k_strided_copy<<<grid, 256, 0, p->stream>>>((const uint4*)src, (uint4*)dst, rows, chunk_bytes / 16,
+                                                    row_bytes / 16, chunks_per_row, plane_bytes / 16);
+    }
+    cudaEventRecord(e1, p->stream);
+    FB_LAUNCH_CHECK();
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *gbs = 2.0 * (double)(planes * plane_bytes) * iters / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(src);
+    cudaFree(dst);
+    return 0;
+}
+
+}  // extern "C"

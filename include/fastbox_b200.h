@@ -1,0 +1,180 @@
+/*
+ * fastbox_b200.h -- C ABI of libfastbox_b200.so (hand-written sm_100a CUDA).
+ *
+ * The reference (philbull/FastBox) is pure Python: its "FFI" for this path is
+ * the set of NumPy/SciPy calls made by fastbox/box.py, fastbox/beams.py and
+ * fastbox/halos.py.  Every entry point below names the reference lines whose
+ * work it replaces.  The Python shim (fastbox_b200/_lib.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a FastBox maintainer would add.
+ *
+ * Conventions
+ *   - return 0 on success, negative on error; message via fb_last_error()
+ *     (thread local).
+ *   - "buffer" arguments may be HOST pointers (pageable or pinned) or DEVICE
+ *     pointers; the library detects which (cudaPointerGetAttributes) and stages
+ *     host buffers through plan-owned device memory.  The caller owns every
+ *     buffer it passes; the library owns only plan workspaces.
+ *   - arrays are C-order [x][y][z], z = line of sight (fastbox/beams.py:70-71).
+ *   - "half spectrum": complex64 planes kx = 0..N/2 of the 3-D DFT of a real
+ *     field, shape [N/2+1][N][N] (axis 0 halved; these are the first N/2+1
+ *     planes of the reference's full `delta_k`, fastbox/box.py:193).
+ *   - all work is enqueued on the plan's stream; results written to host
+ *     buffers are complete when the call returns, results in device buffers
+ *     after fb_sync().
+ *   - a plan is not thread safe; different plans are independent.
+ */
+#ifndef FASTBOX_B200_H
+#define FASTBOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fb_plan fb_plan;
+
+/* ---- k-space multiplier applied in the first pass of an inverse transform -- */
+enum {
+    FB_KIND_PLAIN = 0,      /* field_k * amp                                          */
+    FB_KIND_VEL_X = 1,      /* i k_x / k^2, Nyquist plane of x zeroed  box.py:254,268-274 */
+    FB_KIND_VEL_Y = 2,      /* i k_y / k^2                             box.py:255       */
+    FB_KIND_VEL_Z = 3,      /* i k_z / k^2                             box.py:256       */
+    FB_KIND_POTENTIAL = 4   /* 1 / k^2, DC = 0                         box.py:347-348   */
+};
+
+/* flags for fb_realise / fb_spectrum_to_field */
+enum {
+    FB_F_SQRTPK = 1,        /* multiply by the sqrt(P(k) boxfactor) table   box.py:161-176 */
+    FB_F_FILTER = 2,        /* multiply by the transfer-function table      box.py:374-379 */
+    FB_F_EXP = 4,           /* output exp(scale*field), accumulate its sum  box.py:457     */
+    FB_F_ANTIHERM = 8,      /* take the anti-Hermitian part (gives Im of ifftn)            */
+    FB_F_PK = 16,           /* bin |H|^2/boxfactor of the spectrum being transformed       */
+    FB_F_POLES = 32         /* with FB_F_PK: also l=2,4 Legendre sums                      */
+};
+
+/* Binned-moment output, nb = number of edges; index i follows np.digitize
+ * (fastbox/box.py:758): i = #{edges <= k}; i = 0..nb.  All arrays have nb+1
+ * entries.  mean = sum1/count etc. are formed by the caller exactly like
+ * box.py:761-768.                                                            */
+typedef struct fb_pk_result {
+    uint64_t* count;        /* multiplicity-weighted number of modes            */
+    double* sum1;           /* sum w * p,  p = |d_k|^2 / boxfactor (or Re a b*)  */
+    double* sum2;           /* sum w * p^2                                      */
+    double* sum_l2;         /* sum w * p * L_2(mu)   (nullable)                 */
+    double* sum_l4;         /* sum w * p * L_4(mu)   (nullable)                 */
+} fb_pk_result;
+
+/* ---- plan ---------------------------------------------------------------- */
+/* Replaces CosmoBox.__init__ grid set-up, box.py:76-101,110-127 (the N^3
+ * Kx,Ky,Kz,k arrays are never materialised).  N must be a power of two in
+ * [8, 2048].                                                                 */
+int fb_plan_create(fb_plan** plan, int N, double Lx, double Ly, double Lz, int device);
+int fb_plan_destroy(fb_plan* plan);
+int fb_sync(fb_plan* plan);
+const char* fb_last_error(void);
+const char* fb_version(void);
+/* number of kernels launched by this library since load (process-wide)       */
+uint64_t fb_launch_count(void);
+
+/* ---- slab (multi-GPU) geometry ------------------------------------------- */
+/* Restrict the plan to spectrum planes kx in [a0, a0+na) and real-space rows
+ * y in [y0, y0+ny) (slab decomposition).  Default: everything. */
+int fb_plan_set_slab(fb_plan* plan, int a0, int na, int y0, int ny);
+
+/* ---- memory helpers (the shim keeps fields device resident between calls) - */
+int fb_dev_alloc(void** ptr, size_t bytes);
+int fb_dev_free(void* ptr);
+int fb_host_alloc(void** ptr, size_t bytes);        /* pinned */
+int fb_host_free(void* ptr);
+int fb_copy(fb_plan* plan, void* dst, const void* src, size_t bytes);   /* any direction, async on the plan stream + sync */
+int fb_convert_f64_to_f32(fb_plan* plan, const double* src, float* dst, size_t n);
+int fb_convert_f32_to_f64(fb_plan* plan, const float* src, double* dst, size_t n);
+int fb_device_info(int device, char* name, int name_len, int* sm_count, size_t* total_mem);
+
+/* ---- tables ---------------------------------------------------------------- */
+/* sqrt(P(k) * boxfactor), box.py:161-171.  mode 1: cubic box, exact LUT indexed
+ * by the integer i^2+j^2+l^2 (n entries);  mode 2: table uniform in log2(s),
+ * s = (i/Lx)^2+(j/Ly)^2+(l/Lz)^2, with origin log2s0 and spacing dlog2s.       */
+int fb_set_sqrt_pk(fb_plan* plan, const float* table, long n, int mode, double log2s0, double dlog2s);
+/* transfer function T(k_perp, k_par), box.py:374-378.  Separable form
+ * tperp[(N/2+1)*N] (index a*N+b) times tpar[N]; or dense [(N/2+1)*N*N].
+ * Pass NULLs to clear.                                                        */
+int fb_set_filter(fb_plan* plan, const float* tperp, const float* tpar, const float* tdense);
+/* Bin edges for P(k), box.py:745-758: `thresholds[j]` is the smallest double s
+ * with 2*pi*sqrt(s) >= edge[j] (computed by the shim with NumPy, so that the
+ * device bin index is bit-identical to np.digitize without a device sqrt).    */
+int fb_set_pk_bins(fb_plan* plan, const double* thresholds, int nedges);
+
+/* ---- realise: box.py:174-193 (+ :378, :457, tracers bias) ------------------ */
+/* White noise (re, im) [N][N][N] float32 as drawn at box.py:174-175, or NULL
+ * for on-device Philox4x32-10 noise keyed by (seed, cell index).  Computes
+ *   H = amp * 1/2 [W(k) + conj W(-k)]        (= reference delta_k, box.py:193)
+ *   field = Re ifftn(W * amp) * scale         (box.py:187; scale = bias)
+ * optionally exp() of it with the sum returned in *sum_out (box.py:457-458),
+ * optionally H stored to spec_out (half spectrum) and binned into pk.         */
+int fb_realise(fb_plan* plan, const float* re, const float* im, uint64_t seed, int flags, float scale,
+               float* field_out, void* spec_out, fb_pk_result* pk, double* sum_out);
+
+/* ---- inverse transform of a stored half spectrum: box.py:380, 254-285, 347 -- */
+int fb_spectrum_to_field(fb_plan* plan, const void* spec_half, int flags, int kind, float scale,
+                         float* field_out, double* sum_out);
+/* Same from a FULL complex cube [N][N][N] (complex64) that need not be
+ * Hermitian: part 0 -> Re ifftn(cube*T), part 1 -> Im ifftn(cube*T).          */
+int fb_cube_to_field(fb_plan* plan, const void* cube, int flags, int part, float scale, float* field_out);
+
+/* ---- forward transform + P(k): box.py:736-764 ------------------------------- */
+/* field [N][N][N] float32 -> optional half spectrum, optional binned moments
+ * (auto, or cross with `cross_spec` half spectrum; FB_F_POLES adds l=2,4).    */
+int fb_field_to_spectrum(fb_plan* plan, const float* field, void* spec_out, const void* cross_spec, int flags,
+                         fb_pk_result* pk);
+/* binned moments straight from a stored spectrum.  full_cube = 0: half
+ * spectrum with Hermitian multiplicities; 1: full [N][N][N] cube, weight 1.   */
+int fb_pk_from_spectrum(fb_plan* plan, const void* spec, const void* cross_spec, int full_cube, int flags,
+                        fb_pk_result* pk);
+
+/* ---- elementwise ------------------------------------------------------------- */
+/* field = field * mul + add  (log-normal normalise box.py:458-459, Tb(1+d))   */
+int fb_affine(fb_plan* plan, float* field, size_t n, float mul, float add);
+/* out = exp(scale * in), *sum_out = sum(out)  (box.py:457; halos.py:106)      */
+int fb_exp_sum(fb_plan* plan, const float* in, float* out, size_t n, float scale, double* sum_out);
+/* sum and sum of squares of a field (box.py:944 Parseval)                     */
+int fb_field_moments(fb_plan* plan, const float* field, size_t n, double* sum, double* sumsq);
+
+/* ---- redshift-space remap: box.py:412-437 ------------------------------------ */
+/* z[N] grid coordinates (host, float64); vel_nl nullable (sigma_nl * N(0,1)).  */
+int fb_rsd_remap(fb_plan* plan, const float* delta, const float* vel_z, const float* vel_nl, const double* zgrid,
+                 double Hz, float* out);
+
+/* ---- beam convolution: beams.py:81-87 ----------------------------------------- */
+int fb_beam_convolve(fb_plan* plan, const float* beam, const float* field, float* out);
+
+/* ---- halo counts: halos.py:91-117 ---------------------------------------------- */
+/* nbar/bias kinds: 0 scalar (pointer to 1 float), 1 per-z [N], 2 per-voxel.
+ * mean_exp: mean of exp(bias*delta) when lognormal != 0 (from fb_exp_sum).
+ * uniforms: one float64 U[0,1) per voxel; counts by inversion (fb_poisson.h). */
+int fb_halo_counts(fb_plan* plan, const float* delta, const float* nbar, int nbar_kind, const float* bias,
+                   int bias_kind, int lognormal, double mean_exp, const double* uniforms, int32_t* counts_out,
+                   float* mean_out);
+
+/* ---- building blocks exposed for tests / multi-GPU orchestration ---------------- */
+/* pass = 0: rows (z, contiguous) c2c; 1: columns (y) c2c; sign = -1 fwd / +1 inv;
+ * data: [nplanes][N][N] complex64, in place.                                   */
+int fb_fft_pass_c2c(fb_plan* plan, void* data, int nplanes, int pass, int sign);
+/* x pass, real <-> half complex over planes; ncols = columns per plane.        */
+int fb_fft_pass_x_c2r(fb_plan* plan, const void* spec, float* field, long ncols, int flags, float scale,
+                      double* sum_out);
+int fb_fft_pass_x_r2c(fb_plan* plan, const float* field, void* spec, long ncols);
+/* first pass of realise on the local slab only (rows z + y columns), result in
+ * `work` [na][N][N]; and last passes of the forward transform.                 */
+int fb_realise_local_kspace(fb_plan* plan, uint64_t seed, int flags, void* work, fb_pk_result* pk);
+/* strided HBM copy micro-benchmark: rows of `chunk_bytes`, returns GB/s        */
+int fb_bench_strided_copy(fb_plan* plan, size_t total_bytes, int chunk_bytes, int iters, double* gbs);
+/* time (ms, CUDA events on the plan stream) of the last pipeline call's kernels */
+int fb_last_timings(fb_plan* plan, float* ms, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,65 @@
+/*
+ * fb_poisson.h -- Poisson sampling by inversion from ONE supplied uniform per voxel.
+ *
+ * Replaces np.random.poisson at fastbox/halos.py:116.  NumPy's legacy sampler
+ * consumes a variable number of MT19937 draws per sample, so bit parity with it
+ * cannot be defined; instead the count is a pure function of (lambda, u):
+ *
+ *     p_0 = exp(-lambda);  count = #{ k >= 0 : u > sum_{j<=k} p_j },
+ *     p_k = p_{k-1} * lambda / k
+ *
+ * evaluated in IEEE float64 with round-to-nearest +, *, / only (no FMA
+ * contraction, own exp).  The same header is compiled for the host (gcc
+ * -ffp-contract=off, oracle/fb_oracle.c) and the device (explicit __d*_rn
+ * intrinsics), and restated in NumPy (oracle/restate.py:poisson_from_uniform),
+ * so all three agree bit for bit.  Valid for 0 <= lambda < 700.
+ */
+#ifndef FB_POISSON_H
+#define FB_POISSON_H
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDA_ARCH__
+#define FB_HD __host__ __device__ __forceinline__
+#define FB_MUL(a, b) __dmul_rn((a), (b))
+#define FB_ADD(a, b) __dadd_rn((a), (b))
+#define FB_DIV(a, b) __ddiv_rn((a), (b))
+#else
+#ifdef __CUDACC__
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD static inline
+#endif
+#define FB_MUL(a, b) ((a) * (b))
+#define FB_ADD(a, b) ((a) + (b))
+#define FB_DIV(a, b) ((a) / (b))
+#endif
+
+/* exp(-lam), lam >= 0: n = round(lam/ln2), r = -(lam - n ln2) in two pieces, degree-13 Taylor */
+FB_HD double fb_exp_neg(double lam) {
+    const double n = floor(FB_ADD(FB_MUL(lam, 1.4426950408889634), 0.5));
+    double r = FB_ADD(FB_ADD(lam, -FB_MUL(n, 0.693147180369123816490e+00)), -FB_MUL(n, 1.90821492927058770002e-10));
+    r = -r;
+    const double c[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+                          1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,     1.0 / 6.0,
+                          0.5,               1.0,              1.0};
+    double p = 1.0 / 6227020800.0;
+    for (int i = 0; i < 13; ++i) p = FB_ADD(FB_MUL(p, r), c[i]);
+    return ldexp(p, -(int)n);
+}
+
+FB_HD int32_t fb_poisson_inv(double lam, double u) {
+    if (!(lam > 0.0)) return 0;
+    double p = fb_exp_neg(lam);
+    double cdf = p;
+    int32_t k = 0;
+    while (u > cdf && p > 0.0 && k < 100000) {
+        ++k;
+        p = FB_DIV(FB_MUL(p, lam), (double)k);
+        cdf = FB_ADD(cdf, p);
+    }
+    return k;
+}
+
+#endif
