@@ -67,6 +67,8 @@ SIGNATURES = {
     "fb_realise_local_kspace": (_i, [_vp, _u64, _i, _vp, C.POINTER(PkResult)]),
     "fb_bench_strided_copy": (_i, [_vp, _sz, _i, _i, C.POINTER(_d)]),
     "fb_last_timings": (_i, [_vp, C.POINTER(_f), _i]),
+    "fb_timer_start": (_i, [_vp]),
+    "fb_timer_stop": (_i, [_vp, C.POINTER(_f)]),
 }
 
 _lib = None
@@ -146,6 +148,12 @@ class Plan(object):
         self._keep = []
 
     def close(self):
+        for hp in getattr(self, "_keep", []):
+            try:
+                self.lib.fb_host_free(hp)
+            except Exception:
+                pass
+        self._keep = []
         if getattr(self, "h", None):
             self.lib.fb_plan_destroy(self.h)
             self.h = None
@@ -303,6 +311,23 @@ class Plan(object):
         g = C.c_double()
         check(self.lib.fb_bench_strided_copy(self.h, int(total_bytes), int(chunk_bytes), int(iters), C.byref(g)))
         return g.value
+
+    def timer_start(self):
+        check(self.lib.fb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.lib.fb_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def host_alloc(self, shape, dtype):
+        """Pinned host array (freed with the plan)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(self.lib.fb_host_alloc(C.byref(p), n))
+        self._keep.append(p.value)
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def last_timings(self, n=3):
         ms = (C.c_float * n)()

@@ -638,6 +638,18 @@ int fb_realise_local_kspace(fb_plan* p, uint64_t seed, int flags, void* work, fb
     return 0;
 }
 
+int fb_timer_start(fb_plan* p) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CUDA(cudaEventRecord(p->ev[6], p->stream));
+    return 0;
+}
+int fb_timer_stop(fb_plan* p, float* ms) {
+    FB_CUDA(cudaEventRecord(p->ev[7], p->stream));
+    FB_CUDA(cudaEventSynchronize(p->ev[7]));
+    FB_CUDA(cudaEventElapsedTime(ms, p->ev[6], p->ev[7]));
+    return 0;
+}
+
 int fb_last_timings(fb_plan* p, float* ms, int n) {
     FB_CUDA(cudaStreamSynchronize(p->stream));
     for (int i = 0; i < n; ++i) {

@@ -26,6 +26,21 @@ static int launch_cols_t(fb_plan* p, float2* data, int nplanes, int sign) {
     return 0;
 }
 
+// tile width (columns per CTA).  HBM3e on B200 sustains full bandwidth down to 32-byte row
+// chunks (tools/probe.py), so narrow tiles are preferred: more CTAs per SM overlap load /
+// exchange / store phases.  FB_CZ_COLS / FB_CZ_X override for tuning.
+template <int N>
+static int launch_cols_n(fb_plan* p, float2* data, int nplanes, int sign, int dflt) {
+    const int cz = env_int("FB_CZ_COLS", dflt);
+    if (cz == 4) return launch_cols_t<N, 4>(p, data, nplanes, sign);
+    if (cz == 8) return launch_cols_t<N, 8>(p, data, nplanes, sign);
+    if constexpr (N <= 1024) {
+        if (cz == 16) return launch_cols_t<N, 16>(p, data, nplanes, sign);
+    }
+    set_error("FB_CZ_COLS=%d not available for N=%d", cz, N);
+    return -1;
+}
+
 int launch_cols(fb_plan* p, float2* data, int nplanes, int sign) {
     switch (p->N) {
         case 8: return launch_cols_t<8, 8>(p, data, nplanes, sign);
@@ -33,12 +48,10 @@ int launch_cols(fb_plan* p, float2* data, int nplanes, int sign) {
         case 32: return launch_cols_t<32, 16>(p, data, nplanes, sign);
         case 64: return launch_cols_t<64, 16>(p, data, nplanes, sign);
         case 128: return launch_cols_t<128, 16>(p, data, nplanes, sign);
-        case 256: return launch_cols_t<256, 16>(p, data, nplanes, sign);
-        case 512: return launch_cols_t<512, 16>(p, data, nplanes, sign);
-        case 1024:
-            if (env_int("FB_CZ_COLS", 16) == 8) return launch_cols_t<1024, 8>(p, data, nplanes, sign);
-            return launch_cols_t<1024, 16>(p, data, nplanes, sign);
-        case 2048: return launch_cols_t<2048, 8>(p, data, nplanes, sign);
+        case 256: return launch_cols_n<256>(p, data, nplanes, sign, 16);
+        case 512: return launch_cols_n<512>(p, data, nplanes, sign, 8);
+        case 1024: return launch_cols_n<1024>(p, data, nplanes, sign, 8);
+        case 2048: return launch_cols_n<2048>(p, data, nplanes, sign, 4);
         default: set_error("unsupported N=%d", p->N); return -1;
     }
 }
@@ -64,6 +77,18 @@ static int launch_x_t(fb_plan* p, const XArgs& a, bool inverse) {
     return 0;
 }
 
+template <int N>
+static int launch_x_n(fb_plan* p, const XArgs& a, bool inv, int dflt) {
+    const int cz = env_int("FB_CZ_X", dflt);
+    if (cz == 8) return launch_x_t<N, 8>(p, a, inv);
+    if (cz == 16) return launch_x_t<N, 16>(p, a, inv);
+    if constexpr (N <= 1024) {
+        if (cz == 32) return launch_x_t<N, 32>(p, a, inv);
+    }
+    set_error("FB_CZ_X=%d not available for N=%d", cz, N);
+    return -1;
+}
+
 static int launch_x(fb_plan* p, const XArgs& a, bool inv) {
     switch (p->N) {
         case 8: return launch_x_t<8, 32>(p, a, inv);
@@ -71,12 +96,10 @@ static int launch_x(fb_plan* p, const XArgs& a, bool inv) {
         case 32: return launch_x_t<32, 32>(p, a, inv);
         case 64: return launch_x_t<64, 32>(p, a, inv);
         case 128: return launch_x_t<128, 32>(p, a, inv);
-        case 256: return launch_x_t<256, 32>(p, a, inv);
-        case 512: return launch_x_t<512, 32>(p, a, inv);
-        case 1024:
-            if (env_int("FB_CZ_X", 32) == 16) return launch_x_t<1024, 16>(p, a, inv);
-            return launch_x_t<1024, 32>(p, a, inv);
-        case 2048: return launch_x_t<2048, 16>(p, a, inv);
+        case 256: return launch_x_n<256>(p, a, inv, 32);
+        case 512: return launch_x_n<512>(p, a, inv, 16);
+        case 1024: return launch_x_n<1024>(p, a, inv, 16);
+        case 2048: return launch_x_n<2048>(p, a, inv, 8);
         default: set_error("unsupported N=%d", p->N); return -1;
     }
 }

@@ -149,8 +149,19 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     c[2] = n2;
     c[3] = lo0;
 }
-__device__ __forceinline__ float2 philox_normal_pair(uint64_t seed, uint64_t index) {
-    uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), 0u, 0u};
+__device__ __forceinline__ float2 box_muller(uint32_t x0, uint32_t x1) {
+    // u in (0,1): fl((x0 + 0.5) 2^-32) built from two exact pieces
+    const float u = (float)(x0 >> 8) * 5.9604644775390625e-08f + ((float)(x0 & 0xffu) + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * logf(u));
+    float s, co;
+    sincospif(2.0f * (((float)x1 + 0.5f) * 2.3283064365386963e-10f), &s, &co);
+    return make_float2(r * co, r * s);
+}
+// White noise W = (re, im) of the two cells (index, index+1), index even: one Philox4x32-10
+// block (counter = index/2, key = seed) feeds both cells (words 0,1 -> cell index; 2,3 -> index+1).
+__device__ __forceinline__ void philox_normal_quad(uint64_t seed, uint64_t index, float2& w0, float2& w1) {
+    const uint64_t ctr = index >> 1;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -158,15 +169,8 @@ __device__ __forceinline__ float2 philox_normal_pair(uint64_t seed, uint64_t ind
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    // u in (0,1): (x + 0.5) * 2^-32
-    const float u1 = (float)(c[0] >> 8) * 5.9604644775390625e-08f;                      // exact
-    const float u1lo = ((float)(c[0] & 0xffu) + 0.5f) * 2.3283064365386963e-10f;         // exact
-    const float u = u1 + u1lo;      // fl((x0+0.5)/2^32), > 0
-    const float r = sqrtf(-2.0f * logf(u));
-    float s, co;
-    const float u2 = ((float)c[1] + 0.5f) * 2.3283064365386963e-10f;
-    sincospif(2.0f * u2, &s, &co);
-    return make_float2(r * co, r * s);
+    w0 = box_muller(c[0], c[1]);
+    w1 = box_muller(c[2], c[3]);
 }
 
 }  // namespace fb

@@ -16,12 +16,23 @@ namespace fb {
 
 #define FB_NMAX_TW 4096      // master twiddle table length (forward sign), owned by the plan
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+// FB_DEV functions also compile for the host so the CPU unit test (tests/host_fft_check.cu)
+// can run the exact index logic thread by thread.
+#define FB_DEV __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define FB_LDG(p) __ldg(p)
+#define FB_SYNC() __syncthreads()
+#else
+#define FB_LDG(p) (*(p))
+#define FB_SYNC() ((void)0)
+#endif
+
+FB_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FB_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FB_DEV float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+FB_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // cos(pi*m/16), m = 0..16
 __host__ __device__ constexpr float cos_pi16(int m) {
@@ -38,7 +49,7 @@ __host__ __device__ constexpr float sin_pi16(int m) {   // sin(pi*m/16) = cos(pi
 
 // multiply by exp(S * i * pi * M16 / 16), M16 in [0,16), compile-time
 template <int M16, int S>
-__device__ __forceinline__ float2 ctwiddle(float2 a) {
+FB_DEV float2 ctwiddle(float2 a) {
     if constexpr (M16 == 0) {
         return a;
     } else if constexpr (M16 == 8) {          // * (S i)
@@ -62,11 +73,11 @@ struct Dft;
 
 template <int S>
 struct Dft<1, S> {
-    __device__ __forceinline__ static void run(float2 (&)[1]) {}
+    FB_DEV static void run(float2 (&)[1]) {}
 };
 template <int S>
 struct Dft<2, S> {
-    __device__ __forceinline__ static void run(float2 (&a)[2]) {
+    FB_DEV static void run(float2 (&a)[2]) {
         float2 t = a[0];
         a[0] = cadd(t, a[1]);
         a[1] = csub(t, a[1]);
@@ -74,7 +85,7 @@ struct Dft<2, S> {
 };
 template <int S>
 struct Dft<4, S> {
-    __device__ __forceinline__ static void run(float2 (&a)[4]) {
+    FB_DEV static void run(float2 (&a)[4]) {
         float2 b0 = cadd(a[0], a[2]), b1 = csub(a[0], a[2]);
         float2 b2 = cadd(a[1], a[3]), b3 = ctwiddle<8, S>(csub(a[1], a[3]));
         a[0] = cadd(b0, b2);
@@ -85,7 +96,7 @@ struct Dft<4, S> {
 };
 template <int R, int S>
 struct Dft {
-    __device__ __forceinline__ static void run(float2 (&a)[R]) {
+    FB_DEV static void run(float2 (&a)[R]) {
         constexpr int H = R / 2;
         float2 e[H], o[H];
 #pragma unroll
@@ -98,7 +109,7 @@ struct Dft {
         combine<0>(a, e, o);
     }
     template <int K>
-    __device__ __forceinline__ static void combine(float2 (&a)[R], float2 (&e)[R / 2], float2 (&o)[R / 2]) {
+    FB_DEV static void combine(float2 (&a)[R], float2 (&e)[R / 2], float2 (&o)[R / 2]) {
         if constexpr (K < R / 2) {
             float2 w = ctwiddle<(K * 32) / R, S>(o[K]);
             a[K] = cadd(e[K], w);
@@ -112,22 +123,23 @@ struct Dft {
 // Shared-memory layouts for the exchange buffer.
 //   RowLayout : one FFT per smem row, padded one float2 every 16 (bank spread
 //               for the stride-R Stockham writes).
-//   ColLayout : CZ FFTs interleaved (element-major); conflict free for CZ>=16.
+//   ColLayout : CZ FFTs interleaved (element-major), one pad row every 16 elements so
+//               that the stride-16 Stockham writes of narrow tiles (CZ = 4, 8) spread over banks.
 // ---------------------------------------------------------------------------
 template <int n>
 struct RowLayout {
     static constexpr int ROW = n + n / 16;
     int base;
-    __device__ __forceinline__ int operator()(int i) const { return base + i + (i >> 4); }
+    FB_DEV int operator()(int i) const { return base + i + (i >> 4); }
 };
 template <int CZ>
 struct ColLayout {
     int col;
-    __device__ __forceinline__ int operator()(int i) const { return i * CZ + col; }
+    FB_DEV int operator()(int i) const { return (i + (i >> 4)) * CZ + col; }   // one padded row per 16
 };
 
 template <int n, int P, int R, int Ns, int S>
-__device__ __forceinline__ void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
+FB_DEV void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
     constexpr int T = n / P;
     constexpr int B = P / R;
 #pragma unroll
@@ -140,7 +152,7 @@ __device__ __forceinline__ void fft_stage(float2 (&v)[P], int t, const float2* _
             constexpr int step = (FB_NMAX_TW / (Ns * R));
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                float2 w = __ldg(&tw[r * jm * step]);
+                float2 w = FB_LDG(&tw[r * jm * step]);
                 if (S > 0) w.y = -w.y;
                 a[r] = cmul(a[r], w);
             }
@@ -151,10 +163,9 @@ __device__ __forceinline__ void fft_stage(float2 (&v)[P], int t, const float2* _
     }
 }
 
-// write the outputs of a radix-R stage (previous product Ns) to smem, read back
-// the inputs of the next stage.  Two barriers: the buffer is reused in place.
+// write the outputs of a radix-R stage (previous product Ns) to smem ...
 template <int n, int P, int R, int Ns, class SL>
-__device__ __forceinline__ void fft_exchange(float2 (&v)[P], int t, float2* sm, const SL& sl, bool trailing_sync) {
+FB_DEV void fft_exchange_write(const float2 (&v)[P], int t, float2* sm, const SL& sl) {
     constexpr int T = n / P;
     constexpr int B = P / R;
 #pragma unroll
@@ -164,15 +175,26 @@ __device__ __forceinline__ void fft_exchange(float2 (&v)[P], int t, float2* sm, 
 #pragma unroll
         for (int r = 0; r < R; ++r) sm[sl(j0 + r * Ns)] = v[u + r * B];
     }
-    __syncthreads();
+}
+// ... and read back the inputs of the next stage (thread t owns elements t + T*q).
+template <int n, int P, class SL>
+FB_DEV void fft_exchange_read(float2 (&v)[P], int t, const float2* sm, const SL& sl) {
+    constexpr int T = n / P;
 #pragma unroll
     for (int q = 0; q < P; ++q) v[q] = sm[sl(t + T * q)];
-    if (trailing_sync) __syncthreads();
+}
+// Two barriers: the buffer is reused in place.
+template <int n, int P, int R, int Ns, class SL>
+FB_DEV void fft_exchange(float2 (&v)[P], int t, float2* sm, const SL& sl, bool trailing_sync) {
+    fft_exchange_write<n, P, R, Ns, SL>(v, t, sm, sl);
+    FB_SYNC();
+    fft_exchange_read<n, P, SL>(v, t, sm, sl);
+    if (trailing_sync) FB_SYNC();
 }
 
 // Full length-n transform of the register-resident points.
 template <int n, int P, int R1, int R2, int R3, int S, class SL>
-__device__ __forceinline__ void fft_regs(float2 (&v)[P], int t, float2* sm, const SL& sl,
+FB_DEV void fft_regs(float2 (&v)[P], int t, float2* sm, const SL& sl,
                                          const float2* __restrict__ tw) {
     static_assert(R1 * R2 * R3 == n, "radix product");
     fft_stage<n, P, R1, 1, S>(v, t, tw);

@@ -80,34 +80,36 @@ __device__ __forceinline__ int pk_bin(const PkShared& sh, int nedges, double s) 
 }
 
 // One mode per lane; lanes of a warp are aggregated by bin before touching smem.
-// w = multiplicity (uniform over the warp), p = power, mu2 = (k_par/k)^2.
+// w = multiplicity of the lane's mode (1 or 2), p = power, mu2 = (k_par/k)^2.
 __device__ __forceinline__ void pk_accumulate(PkShared& sh, int bin, float w, float p, float mu2, bool poles,
                                               bool valid) {
     const unsigned full = 0xffffffffu;
     unsigned todo = __ballot_sync(full, valid);
     const int lane = threadIdx.x & 31;
+    const unsigned wi = (unsigned)(w + 0.5f);
     while (todo) {
         const int leader = __ffs(todo) - 1;
         const int lb = __shfl_sync(full, bin, leader);
         const bool mine = valid && (bin == lb);
         const unsigned grp = __ballot_sync(full, mine);
+        const unsigned cnt = __reduce_add_sync(full, mine ? wi : 0u);
         const double pd = mine ? (double)p : 0.0;
-        double a1 = warp_sum(pd);
-        double a2 = warp_sum(pd * pd);
+        const double wp = (double)w * pd;
+        double a1 = warp_sum(wp);
+        double a2 = warp_sum(wp * pd);
         double b2 = 0.0, b4 = 0.0;
         if (poles) {
             const double m2 = (double)mu2;
-            b2 = warp_sum(pd * (1.5 * m2 - 0.5));
-            b4 = warp_sum(pd * ((35.0 * m2 * m2 - 30.0 * m2 + 3.0) * 0.125));
+            b2 = warp_sum(wp * (1.5 * m2 - 0.5));
+            b4 = warp_sum(wp * ((35.0 * m2 * m2 - 30.0 * m2 + 3.0) * 0.125));
         }
         if (lane == leader) {
-            const double wd = (double)w;
-            atomicAdd(&sh.cnt[lb], (unsigned long long)(__popc(grp)) * (unsigned long long)(w + 0.5f));
-            atomicAdd(&sh.s1[lb], wd * a1);
-            atomicAdd(&sh.s2[lb], wd * a2);
+            atomicAdd(&sh.cnt[lb], (unsigned long long)cnt);
+            atomicAdd(&sh.s1[lb], a1);
+            atomicAdd(&sh.s2[lb], a2);
             if (poles) {
-                atomicAdd(&sh.l2[lb], wd * b2);
-                atomicAdd(&sh.l4[lb], wd * b4);
+                atomicAdd(&sh.l2[lb], b2);
+                atomicAdd(&sh.l4[lb], b4);
             }
         }
         todo &= ~grp;

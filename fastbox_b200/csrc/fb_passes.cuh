@@ -39,6 +39,114 @@ struct RowsArgs {
 };
 
 // ---------------------------------------------------------------------------
+// Row kernels.  The k-space prologue / epilogue works in NATURAL order: thread t of a
+// row owns the P consecutive modes c = P*t .. P*t+P-1 (vectorised 16-byte global
+// accesses; the P(k) bin changes at most once or twice along such a run, so moments
+// are accumulated in registers and flushed once per thread).  The FFT itself works in
+// Stockham order (thread t owns t + T*q); one shared-memory transpose connects the two.
+// ---------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void load_run(const float* __restrict__ p, float (&out)[P]) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < P / 4; ++i) {
+        const float4 v = __ldg(p4 + i);
+        out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+    }
+}
+template <int P>
+__device__ __forceinline__ void load_run(const float2* __restrict__ p, float2 (&out)[P]) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < P / 2; ++i) {
+        const float4 v = __ldg(p4 + i);
+        out[2 * i] = make_float2(v.x, v.y);
+        out[2 * i + 1] = make_float2(v.z, v.w);
+    }
+}
+template <int P>
+__device__ __forceinline__ void store_run(float2* __restrict__ p, const float2 (&in)[P]) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+#pragma unroll
+    for (int i = 0; i < P / 2; ++i) p4[i] = make_float4(in[2 * i].x, in[2 * i].y, in[2 * i + 1].x, in[2 * i + 1].y);
+}
+
+// running P(k) moments of one thread while it walks along c
+struct PkWalk {
+    int bin;
+    unsigned cnt;
+    double s1, s2, l2, l4;      // float64: a bin holding only a Hermitian pair gets stddev == 0 exactly
+};
+
+__device__ __forceinline__ void pk_walk_flush_thread(PkShared& sh, PkWalk& w, bool poles) {
+    if (w.cnt) {
+        atomicAdd(&sh.cnt[w.bin], (unsigned long long)w.cnt);
+        atomicAdd(&sh.s1[w.bin], w.s1);
+        atomicAdd(&sh.s2[w.bin], w.s2);
+        if (poles) {
+            atomicAdd(&sh.l2[w.bin], w.l2);
+            atomicAdd(&sh.l4[w.bin], w.l4);
+        }
+    }
+    w.cnt = 0u;
+    w.s1 = w.s2 = w.l2 = w.l4 = 0.0;
+}
+
+// add mode (s, p) with multiplicity wf to the walk; s is monotone along a run so the bin moves by
+// single steps (both directions are handled: |m_c| decreases for c >= N/2)
+__device__ __forceinline__ void pk_walk_add(PkShared& sh, PkWalk& w, int nedges, double s, float p, float wf,
+                                            float mu2, bool poles) {
+    int nb = w.bin;
+    while (nb < nedges && s >= sh.thr[nb]) ++nb;
+    while (nb > 0 && s < sh.thr[nb - 1]) --nb;
+    if (nb != w.bin) {
+        pk_walk_flush_thread(sh, w, poles);
+        w.bin = nb;
+    }
+    const double pd = (double)p, wp = (double)wf * pd;
+    w.cnt += (unsigned)(wf + 0.5f);
+    w.s1 += wp;
+    w.s2 += wp * pd;
+    if (poles) {
+        const double m2 = (double)mu2;
+        w.l2 += wp * (1.5 * m2 - 0.5);
+        w.l4 += wp * ((35.0 * m2 * m2 - 30.0 * m2 + 3.0) * 0.125);
+    }
+}
+
+// end of the run: lanes of a warp holding the same bin are combined before touching smem
+__device__ __forceinline__ void pk_walk_flush_warp(PkShared& sh, const PkWalk& w, bool poles, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const bool have = valid && w.cnt > 0u;
+    unsigned todo = __ballot_sync(full, have);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lb = __shfl_sync(full, w.bin, leader);
+        const bool mine = have && (w.bin == lb);
+        const unsigned grp = __ballot_sync(full, mine);
+        const unsigned cnt = __reduce_add_sync(full, mine ? w.cnt : 0u);
+        const double a1 = warp_sum(mine ? w.s1 : 0.0);
+        const double a2 = warp_sum(mine ? w.s2 : 0.0);
+        double b2 = 0.0, b4 = 0.0;
+        if (poles) {
+            b2 = warp_sum(mine ? w.l2 : 0.0);
+            b4 = warp_sum(mine ? w.l4 : 0.0);
+        }
+        if (lane == leader) {
+            atomicAdd(&sh.cnt[lb], (unsigned long long)cnt);
+            atomicAdd(&sh.s1[lb], a1);
+            atomicAdd(&sh.s2[lb], a2);
+            if (poles) {
+                atomicAdd(&sh.l2[lb], b2);
+                atomicAdd(&sh.l4[lb], b4);
+            }
+        }
+        todo &= ~grp;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // rows, inverse.  grid = ceil(na*N / RB), block = 256
 // ---------------------------------------------------------------------------
 template <int N, int SRC>
@@ -69,55 +177,97 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_inv(const RowsArgs
     const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
     const double sab = do_pk ? __dadd_rn(A.K.ax[a], A.K.ay[b]) : 0.0;
     const bool velocity = (A.kind >= FB_KIND_VEL_X && A.kind <= FB_KIND_VEL_Z);
+    const int c0 = P * t;                          // natural-order run of this thread
+    const int mstart = N - c0 - P;                 // mirror block: cells mstart .. mstart+P-1  (c -> N-c)
+    const int cm0 = (N - c0) & (N - 1);            // mirror of the first cell of the run
 
-    float2 v[P];
+    float2 h[P];
+    if constexpr (SRC == SRC_SPEC) {
+        load_run<P>(A.src + row_local + c0, h);
+    } else {
+        float2 g[P], mm[P], gm0;
+        if constexpr (SRC == SRC_NOISE) {
+            float r[P], i[P];
+            load_run<P>(A.re + row_g + c0, r);
+            load_run<P>(A.im + row_g + c0, i);
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int c = t + T * q;
-        const int cm = (N - c) & (N - 1);
-        float2 h;
-        if constexpr (SRC == SRC_SPEC) {
-            h = A.src[row_local + c];
-            const float amp = k_amp(A.K, A.flags, A.kind, a, b, c, c);
-            h.x *= amp;
-            h.y *= amp;
+            for (int e = 0; e < P; ++e) g[e] = make_float2(r[e], i[e]);
+            load_run<P>(A.re + row_m + mstart, r);
+            load_run<P>(A.im + row_m + mstart, i);
+#pragma unroll
+            for (int e = 0; e < P; ++e) mm[e] = make_float2(r[e], i[e]);
+            gm0 = make_float2(__ldg(&A.re[row_m + cm0]), __ldg(&A.im[row_m + cm0]));
+        } else if constexpr (SRC == SRC_PHILOX) {
+#pragma unroll
+            for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_g + c0 + e, g[e], g[e + 1]);
+#pragma unroll
+            for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_m + mstart + e, mm[e], mm[e + 1]);
+            float2 q0, q1;
+            philox_normal_quad(A.seed, (row_m + cm0) & ~(size_t)1, q0, q1);
+            gm0 = ((row_m + cm0) & 1) ? q1 : q0;
         } else {
-            float2 g, gm;
-            if constexpr (SRC == SRC_NOISE) {
-                g = make_float2(__ldg(&A.re[row_g + c]), __ldg(&A.im[row_g + c]));
-                gm = make_float2(__ldg(&A.re[row_m + cm]), __ldg(&A.im[row_m + cm]));
-            } else if constexpr (SRC == SRC_PHILOX) {
-                g = philox_normal_pair(A.seed, row_g + c);
-                gm = philox_normal_pair(A.seed, row_m + cm);
-            } else {
-                g = __ldg(&A.src[row_g + c]);
-                gm = __ldg(&A.src[row_m + cm]);
-            }
-            const float amp = k_amp(A.K, A.flags, A.kind, a, b, c, c);
-            float ampm = amp;
-            if constexpr (SRC == SRC_CUBE) {
-                if (A.flags & FB_F_FILTER) ampm = k_amp(A.K, A.flags, A.kind, a, b, c, cm);
-            }
-            g.x *= amp; g.y *= amp;
-            gm.x *= ampm; gm.y *= ampm;
-            if (A.flags & FB_F_ANTIHERM)        // (G(k) - conj G(-k)) / (2i)
-                h = make_float2(0.5f * (g.y + gm.y), -0.5f * (g.x - gm.x));
-            else                                // (G(k) + conj G(-k)) / 2
-                h = make_float2(0.5f * (g.x + gm.x), 0.5f * (g.y - gm.y));
+            load_run<P>(A.src + row_g + c0, g);
+            load_run<P>(A.src + row_m + mstart, mm);
+            gm0 = __ldg(&A.src[row_m + cm0]);
         }
-        if (velocity) h = make_float2(-h.y, h.x);          // * i, box.py:254-256
-        if (A.spec_out && rvalid) A.spec_out[row_local + c] = h;
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            const float2 gm = (e == 0) ? gm0 : mm[P - e];
+            if (A.flags & FB_F_ANTIHERM)        // (G(k) - conj G(-k)) / (2i)
+                h[e] = make_float2(0.5f * (g[e].y + gm.y), -0.5f * (g[e].x - gm.x));
+            else                                // (G(k) + conj G(-k)) / 2
+                h[e] = make_float2(0.5f * (g[e].x + gm.x), 0.5f * (g[e].y - gm.y));
+            if constexpr (SRC == SRC_CUBE) {
+                // a k_par-odd filter multiplies G(k) and G(-k) differently: apply it before combining
+                if (A.flags & FB_F_FILTER) {
+                    const int c = c0 + e, cm = (N - c) & (N - 1);
+                    const float f = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, c);
+                    const float fm = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, cm);
+                    const float2 x = make_float2(g[e].x * f, g[e].y * f), y = make_float2(gm.x * fm, gm.y * fm);
+                    if (A.flags & FB_F_ANTIHERM)
+                        h[e] = make_float2(0.5f * (x.y + y.y), -0.5f * (x.x - y.x));
+                    else
+                        h[e] = make_float2(0.5f * (x.x + y.x), 0.5f * (x.y - y.y));
+                }
+            }
+        }
+    }
+    PkWalk walk;
+    walk.bin = 0;
+    walk.cnt = 0u;
+    walk.s1 = walk.s2 = walk.l2 = walk.l4 = 0.0;
+    const int amp_flags = (SRC == SRC_CUBE) ? (A.flags & ~FB_F_FILTER) : A.flags;
+#pragma unroll
+    for (int e = 0; e < P; ++e) {
+        const int c = c0 + e;
+        const float amp = k_amp(A.K, amp_flags, A.kind, a, b, c, c);
+        float2 v = make_float2(h[e].x * amp, h[e].y * amp);
+        if (velocity) v = make_float2(-v.y, v.x);          // * i, box.py:254-256
+        h[e] = v;
         if (do_pk) {
             const double azc = A.K.az[c];
             const double s = __dadd_rn(sab, azc);
-            const int bin = pk_bin(pks, A.K.nedges, s);
-            const float p = (h.x * h.x + h.y * h.y) * (float)A.K.inv_boxfactor;
+            if (e == 0) walk.bin = pk_bin(pks, A.K.nedges, s);
+            const float p = (v.x * v.x + v.y * v.y) * (float)A.K.inv_boxfactor;
             const float mu2 = (poles && s > 0.0) ? (float)azc / (float)s : 0.f;
-            pk_accumulate(pks, bin, wmult, p, mu2, poles, rvalid);
+            if (rvalid) pk_walk_add(pks, walk, A.K.nedges, s, p, wmult, mu2, poles);
         }
-        v[q] = h;
     }
+    if (A.spec_out && rvalid) store_run<P>(A.spec_out + row_local + c0, h);
+    if (do_pk) pk_walk_flush_warp(pks, walk, poles, rvalid);
+
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
+    float2 v[P];
+    if constexpr (T > 1) {
+#pragma unroll
+        for (int e = 0; e < P; ++e) sm[sl(c0 + e)] = h[e];
+        __syncthreads();
+        fft_exchange_read<N, P>(v, t, sm, sl);
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int e = 0; e < P; ++e) v[e] = h[e];
+    }
     fft_regs<N, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, A.tw);
 #pragma unroll
     for (int q = 0; q < P; ++q)
@@ -157,29 +307,47 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_fwd(const RowsArgs
     for (int q = 0; q < P; ++q) v[q] = A.work[row_local + t + T * q];
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
     fft_regs<N, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, A.tw);
-    const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
-    const double sab = do_pk ? __dadd_rn(A.K.ax[a], A.K.ay[b]) : 0.0;
+    // back to natural order: thread owns c0 .. c0+P-1
+    const int c0 = P * t;
+    float2 h[P];
+    if constexpr (T > 1) {
+        __syncthreads();
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int c = t + T * q;
-        const float2 h = v[q];
-        if (A.spec_out && rvalid) A.spec_out[row_local + c] = h;
-        if (do_pk) {
+        for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < P; ++e) h[e] = sm[sl(c0 + e)];
+    } else {
+#pragma unroll
+        for (int e = 0; e < P; ++e) h[e] = v[e];
+    }
+    if (A.spec_out && rvalid) store_run<P>(A.spec_out + row_local + c0, h);
+    if (do_pk) {
+        const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
+        const double sab = __dadd_rn(A.K.ax[a], A.K.ay[b]);
+        PkWalk walk;
+        walk.bin = 0;
+        walk.cnt = 0u;
+        walk.s1 = walk.s2 = walk.l2 = walk.l4 = 0.0;
+        float2 x[P];
+        if (A.cross) load_run<P>(A.cross + row_local + c0, x);
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            const int c = c0 + e;
             const double azc = A.K.az[c];
             const double s = __dadd_rn(sab, azc);
-            const int bin = pk_bin(pks, A.K.nedges, s);
+            if (e == 0) walk.bin = pk_bin(pks, A.K.nedges, s);
             float p;
-            if (A.cross) {
-                const float2 x = A.cross[row_local + c];
-                p = (h.x * x.x + h.y * x.y) * (float)A.K.inv_boxfactor;
-            } else {
-                p = (h.x * h.x + h.y * h.y) * (float)A.K.inv_boxfactor;
-            }
+            if (A.cross)
+                p = (h[e].x * x[e].x + h[e].y * x[e].y) * (float)A.K.inv_boxfactor;
+            else
+                p = (h[e].x * h[e].x + h[e].y * h[e].y) * (float)A.K.inv_boxfactor;
             const float mu2 = (poles && s > 0.0) ? (float)azc / (float)s : 0.f;
-            pk_accumulate(pks, bin, wmult, p, mu2, poles, rvalid);
+            if (rvalid) pk_walk_add(pks, walk, A.K.nedges, s, p, wmult, mu2, poles);
         }
+        pk_walk_flush_warp(pks, walk, poles, rvalid);
+        pk_shared_flush(pks, A.K, A.pk, poles);
     }
-    if (do_pk) pk_shared_flush(pks, A.K, A.pk, poles);
 }
 
 // ---------------------------------------------------------------------------
@@ -190,7 +358,7 @@ template <int N, int CZ>
 struct ColGeom {
     using C = FftCfg<N>;
     static constexpr int THREADS = CZ * C::T;
-    static constexpr size_t SMEM = (size_t)N * CZ * sizeof(float2);
+    static constexpr size_t SMEM = (size_t)(N + N / 16) * CZ * sizeof(float2);
 };
 
 template <int N, int CZ, int S>
@@ -237,7 +405,7 @@ struct XGeom {
     static constexpr int M = N / 2;
     using C = FftCfg<M>;
     static constexpr int THREADS = CZ * C::T;
-    static constexpr size_t SMEM = (size_t)M * CZ * sizeof(float2);
+    static constexpr size_t SMEM = (size_t)(M + M / 16) * CZ * sizeof(float2);
 };
 
 template <int N, int CZ>

@@ -171,6 +171,9 @@ int fb_fft_pass_x_r2c(fb_plan* plan, const float* field, void* spec, long ncols)
 int fb_realise_local_kspace(fb_plan* plan, uint64_t seed, int flags, void* work, fb_pk_result* pk);
 /* strided HBM copy micro-benchmark: rows of `chunk_bytes`, returns GB/s        */
 int fb_bench_strided_copy(fb_plan* plan, size_t total_bytes, int chunk_bytes, int iters, double* gbs);
+/* CUDA-event stopwatch on the plan's stream (bench.py times the step loop with it) */
+int fb_timer_start(fb_plan* plan);
+int fb_timer_stop(fb_plan* plan, float* ms);
 /* time (ms, CUDA events on the plan stream) of the last pipeline call's kernels */
 int fb_last_timings(fb_plan* plan, float* ms, int n);
 

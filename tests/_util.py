@@ -14,8 +14,9 @@ TOL = 1e-5                                                       # north_star to
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    cplx = np.iscomplexobj(a) or np.iscomplexobj(b)
+    a = np.asarray(a, dtype=np.complex128 if cplx else np.float64)
+    b = np.asarray(b, dtype=np.complex128 if cplx else np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 

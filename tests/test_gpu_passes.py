@@ -14,8 +14,7 @@ SIZES = [8, 16, 32, 64, 128, 256]
 TOL = 1e-5
 
 
-def rel_l2(a, b):
-    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+from _util import rel_l2
 
 
 @pytest.mark.parametrize("N", SIZES + [512])

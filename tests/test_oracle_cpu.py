@@ -1,0 +1,151 @@
+"""
+CPU tests (no GPU): pin oracle/restate.py against (a) the golden vectors produced by the
+UNMODIFIED reference (tests/golden, oracle/make_golden.py) and (b) the live reference modules
+when /root/reference is present.  Also the plain-C oracle vs the NumPy restatement.
+"""
+import ctypes
+import os
+import subprocess
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+from oracle import restate as R
+
+from _util import draw_noise, load_golden, pk_function, transfer_fn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = ["n16_cubic", "n16_cuboid", "n32_gpc"]
+
+
+def _L(g):
+    return tuple(float(x) for x in g["L"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_port_reproduces_reference_golden(name):
+    g = load_golden(name)
+    N, L = int(g["N"]), _L(g)
+    scale = tuple(g["scale"]) if g["scale"].size == 3 else float(g["scale"][0])
+    assert R.box_lengths(scale, N) == L
+    assert R.boxfactor(N, *L) == float(g["boxfactor"])
+    assert R.kmin_kmax(N, *L) == (float(g["kmin"]), float(g["kmax"]))
+    re, im = draw_noise(int(g["seed"]), N)
+    _, pkf = pk_function(float(g["redshift"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dx, dk = R.realise_density_port(re, im, pkf, N, *L)
+        assert np.array_equal(dx, g["delta_x"])                       # bitwise
+        assert np.array_equal(dk[:N // 2 + 1], g["delta_k_half"])
+        for nb in (20, 50):
+            kc, pk, err, cnt, idx = R.binned_power_spectrum_port(dk, N, *L, nbins=nb, return_raw=True)
+            assert np.array_equal(kc, g["pk%d_k" % nb])
+            assert np.array_equal(pk, g["pk%d_p" % nb], equal_nan=True)
+            assert np.array_equal(err, g["pk%d_e" % nb], equal_nan=True)
+            assert np.array_equal(np.bincount(idx, minlength=nb + 1), g["pk%d_counts" % nb])
+        assert np.array_equal(R.apply_transfer_fn_port(dk, transfer_fn, N, *L).real, g["transfer"])
+        assert np.array_equal(R.lognormal(dx * float(g["bias_HI"])), g["lognormal"])
+        rs = R.redshift_space_density(g["lognormal"], g["vel_z"], g["z_grid"], float(g["Hz"]))
+        assert np.allclose(rs, g["rsd0"], rtol=1e-13, atol=1e-13)
+        np.random.seed(int(g["seed"]) + 100)
+        vnl = 120. * np.random.normal(0., 1., (N, N, N))
+        rs = R.redshift_space_density(g["lognormal"], g["vel_z"], g["z_grid"], float(g["Hz"]), vnl)
+        assert np.allclose(rs, g["rsd120"], rtol=1e-13, atol=1e-13)
+        from _util import DEFAULT_COSMO  # noqa: F401
+        bc = R.convolve_fft(__import__("oracle.make_golden", fromlist=["beam_cube"]).beam_cube(N), g["rsd0"])
+        assert np.allclose(bc, g["beam_conv"], rtol=1e-12, atol=1e-14)
+        assert np.allclose(R.halo_mean_count(dx, 1e-3, 1.2, *L, lognormal_tf=True), g["halo_mean_ln"], rtol=1e-14)
+        assert np.allclose(R.halo_mean_count(dx, np.linspace(1e-3, 2e-3, N), 1.2, *L), g["halo_mean_lin"], rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_lean_restatement_matches_port(name):
+    g = load_golden(name)
+    N, L = int(g["N"]), _L(g)
+    re, im = draw_noise(int(g["seed"]), N)
+    _, pkf = pk_function(float(g["redshift"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dx, half = R.realise_density_lean(re, im, pkf, N, *L)
+        assert np.linalg.norm(dx - g["delta_x"]) / np.linalg.norm(g["delta_x"]) < 1e-14
+        assert np.abs(half - g["delta_k_half"]).max() / np.abs(g["delta_k_half"]).max() < 1e-14
+        assert np.abs(R.expand_half_axis0(half)[N // 2 + 1:] - np.fft.fftn(g["delta_x"])[N // 2 + 1:]).max() \
+            / np.abs(half).max() < 1e-13
+        for nb in (20, 50):
+            kc, pk, err, cnt = R.binned_power_spectrum_lean(half, N, *L, nbins=nb)
+            assert np.array_equal(cnt[:nb], g["pk%d_counts" % nb][:nb])
+            ref = g["pk%d_p" % nb]
+            m = ~np.isnan(ref)
+            assert np.array_equal(np.isnan(pk), np.isnan(ref))
+            assert np.all(np.abs(pk[m] - ref[m]) <= 1e-13 * np.abs(ref[m]))
+        # Parseval by-product (box.py:944-946)
+        s1 = np.sum(dx ** 2.) * N ** 3.
+        assert abs(s1 / g["parseval"][1] - 1) < 1e-12
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_restatement_against_live_reference():
+    """Run the unmodified reference side by side on a configuration the fixtures do not hold."""
+    box_m = ref_loader.load("box")
+    N, scale, seed, z = 24 if False else 16, (3e2, 2e2, 5e2), 41, 0.4
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(seed)
+        b = box_m.CosmoBox(cosmo=box_m.default_cosmo, box_scale=scale, nsamp=N, redshift=z, realise_now=False)
+        b.realise_density()
+        re, im = draw_noise(seed, N)
+        _, pkf = pk_function(z)
+        L = R.box_lengths(scale, N)
+        dx, dk = R.realise_density_port(re, im, pkf, N, *L)
+        assert np.array_equal(dx, b.delta_x)
+        kc, pk, err = b.binned_power_spectrum(nbins=30)
+        kc2, pk2, err2 = R.binned_power_spectrum_port(dk, N, *L, nbins=30)
+        assert np.array_equal(pk, pk2, equal_nan=True)
+        assert np.array_equal(R.k_grid(N, *L), b.k)
+        hp = lambda kperp, kpar: 1. - np.exp(-0.5 * (np.abs(kpar) / 0.009) ** 3.)     # example_endtoend.py:133
+        assert np.array_equal(R.apply_transfer_fn_port(dk, hp, N, *L), b.apply_transfer_fn(b.delta_k, hp))
+        assert np.allclose(R.smooth_field_port(dk, 8.0, 0.7, N, *L), b.smooth_field(b.delta_k, 8.0), atol=1e-15)
+
+
+def test_c_oracle_matches_numpy_restatement():
+    subprocess.check_call(["make", "-s"], cwd=os.path.join(ROOT, "oracle"))
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libfb_oracle.so"))
+    rng = np.random.default_rng(3)
+    lam = np.concatenate([rng.uniform(0, 5, 20000), rng.uniform(5, 120, 20000), [0.0, 1e-12, 650.0]])
+    u = rng.random(lam.size)
+    out = np.zeros(lam.size, np.int32)
+    lib.fb_oracle_poisson(lam.ctypes.data_as(ctypes.c_void_p), u.ctypes.data_as(ctypes.c_void_p),
+                          ctypes.c_long(lam.size), out.ctypes.data_as(ctypes.c_void_p))
+    ref = R.poisson_from_uniform(lam, u)
+    assert np.array_equal(out.astype(np.int64), ref)
+    # distributional sanity vs np.random.poisson (the reference's sampler, halos.py:116)
+    lam1 = np.full(200000, 7.5)
+    k = R.poisson_from_uniform(lam1, rng.random(lam1.size))
+    assert abs(k.mean() - 7.5) < 0.03 and abs(k.var() - 7.5) < 0.1
+    # exp(-lam) restatement is accurate to 1 ulp-ish
+    lib.fb_oracle_exp_neg.restype = ctypes.c_double
+    lib.fb_oracle_exp_neg.argtypes = [ctypes.c_double]
+    for x in (0.0, 1e-3, 0.5, 3.0, 30.0, 200.0, 650.0):
+        assert lib.fb_oracle_exp_neg(x) == float(R._exp_neg(np.array(x)))
+        assert abs(lib.fb_oracle_exp_neg(x) / np.exp(-x) - 1) < 5e-16
+    # digitize restatement in C == np.digitize on the reference's k array
+    N, L = 16, (1e2, 2e2, 1e3)
+    edges = R.pk_bin_edges(N, *L, nbins=20)
+    counts = np.zeros(21, np.int64)
+    lib.fb_oracle_digitize_counts(ctypes.c_int(N), ctypes.c_double(L[0]), ctypes.c_double(L[1]),
+                                  ctypes.c_double(L[2]), edges.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(20),
+                                  counts.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(counts, np.bincount(R.digitize_modes(N, *L, edges), minlength=21))
+
+
+def test_philox_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): counter/key -> output."""
+    out = R.philox4x32(np.zeros((1, 4), np.uint32), np.zeros(2, np.uint32))
+    assert [hex(int(x)) for x in out[0]] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    ctr = np.full((1, 4), 0xffffffff, np.uint32)
+    out = R.philox4x32(ctr, np.full(2, 0xffffffff, np.uint32))
+    assert [hex(int(x)) for x in out[0]] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    re, im = R.philox_normals(42, np.arange(200000))
+    assert abs(re.mean()) < 0.01 and abs(re.std() - 1) < 0.01 and abs(np.corrcoef(re, im)[0, 1]) < 0.01
