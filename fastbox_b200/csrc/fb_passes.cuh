@@ -146,11 +146,121 @@ __device__ __forceinline__ void pk_walk_flush_warp(PkShared& sh, const PkWalk& w
     }
 }
 
+// Per-run multiplier amp[e] for modes c0+e (sqrt(P) LUT, filter, velocity / potential factor).
+// Each option is ONE warp-uniform branch around an unrolled loop (no per-element flag tests).
+template <int N, int P>
+__device__ __forceinline__ void run_amp(const KSpace& K, int flags, int kind, int a, int b, int c0, float base,
+                                        float (&amp)[P]) {
+    const int ma = mode_number(a, N), mb = mode_number(b, N);
+#pragma unroll
+    for (int e = 0; e < P; ++e) amp[e] = base;
+    if (flags & FB_F_SQRTPK) {
+        if (K.sqrtp_mode == 1) {
+            const float* lut = K.sqrtp + (ma * ma + mb * mb);
+#pragma unroll
+            for (int e = 0; e < P; ++e) {
+                const int mc = mode_number(c0 + e, N);
+                amp[e] *= __ldg(lut + mc * mc);
+            }
+        } else {
+            const float sab = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2;
+#pragma unroll
+            for (int e = 0; e < P; ++e) {
+                const int mc = mode_number(c0 + e, N);
+                const float s = sab + (float)(mc * mc) * K.inv_lz2;
+                float val = 0.f;                                   // nan_to_num(P(0)) = 0, box.py:167
+                if (s > 0.f) {
+                    float x = (log2f(s) - K.log2s0) * K.inv_dlog2s;
+                    x = fminf(fmaxf(x, 0.f), (float)(K.sqrtp_n - 1) - 1e-3f);
+                    const int i0 = (int)x;
+                    const float y0 = __ldg(&K.sqrtp[i0]), y1 = __ldg(&K.sqrtp[i0 + 1]);
+                    val = fmaf(x - (float)i0, y1 - y0, y0);
+                }
+                amp[e] *= val;
+            }
+        }
+    }
+    if (flags & FB_F_FILTER) {
+        if (K.tdense) {
+            float tf[P];
+            load_run<P>(K.tdense + ((size_t)a * N + b) * N + c0, tf);
+#pragma unroll
+            for (int e = 0; e < P; ++e) amp[e] *= tf[e];
+        } else {
+            float tf[P];
+            load_run<P>(K.tpar + c0, tf);
+            const float tp = __ldg(&K.tperp[a * N + b]);
+#pragma unroll
+            for (int e = 0; e < P; ++e) amp[e] *= tp * tf[e];
+        }
+    }
+    if (kind != FB_KIND_PLAIN) {
+        const float sab = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2;
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            const int mc = mode_number(c0 + e, N);
+            const float k2 = 39.478417604357434f * (sab + (float)(mc * mc) * K.inv_lz2);    // (2 pi)^2 s
+            const float ik2 = k2 > 0.f ? 1.f / k2 : 0.f;          // nan_to_num at k = 0, box.py:257-259
+            float comp = 1.f;
+            int m = 1;
+            if (kind == FB_KIND_VEL_X) { comp = (float)ma * K.two_pi_over_lx; m = ma; }
+            else if (kind == FB_KIND_VEL_Y) { comp = (float)mb * K.two_pi_over_ly; m = mb; }
+            else if (kind == FB_KIND_VEL_Z) { comp = (float)mc * K.two_pi_over_lz; m = mc; }
+            if (kind != FB_KIND_POTENTIAL && m == -N / 2) comp = 0.f;                       // box.py:268-274
+            amp[e] *= comp * ik2;
+        }
+    }
+}
+
+// P(k) moments of one natural-order run h[0..P) (modes c0..c0+P-1 of row (a,b)), optionally
+// crossed with x[].  Fast path: first and last mode of the run fall in the same bin (s is monotone
+// along a run when T > 1), so no per-mode bin search is needed.
+template <int N, int P, bool MONOTONE>
+__device__ __forceinline__ void run_pk(PkShared& pks, const KSpace& K, int a, int b, int c0, const float2 (&h)[P],
+                                       const float2* x, bool poles, bool rvalid) {
+    const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
+    const double sab = __dadd_rn(K.ax[a], K.ay[b]);
+    const float invb = (float)K.inv_boxfactor;
+    PkWalk walk;
+    walk.bin = 0;
+    walk.cnt = 0u;
+    walk.s1 = walk.s2 = walk.l2 = walk.l4 = 0.0;
+    const double s_first = __dadd_rn(sab, K.az[c0]), s_last = __dadd_rn(sab, K.az[c0 + P - 1]);
+    const int b0 = pk_bin(pks, K.nedges, s_first), b1 = pk_bin(pks, K.nedges, s_last);
+    if (MONOTONE && b0 == b1 && !poles) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            const float p = x ? (h[e].x * x[e].x + h[e].y * x[e].y) * invb : (h[e].x * h[e].x + h[e].y * h[e].y) * invb;
+            const double pd = (double)p;
+            s1 += pd;
+            s2 = fma(pd, pd, s2);
+        }
+        if (rvalid) {
+            walk.bin = b0;
+            walk.cnt = (unsigned)P * (unsigned)(wmult + 0.5f);
+            walk.s1 = (double)wmult * s1;
+            walk.s2 = (double)wmult * s2;
+        }
+    } else {
+        walk.bin = b0;
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            const double azc = K.az[c0 + e];
+            const double s = __dadd_rn(sab, azc);
+            const float p = x ? (h[e].x * x[e].x + h[e].y * x[e].y) * invb : (h[e].x * h[e].x + h[e].y * h[e].y) * invb;
+            const float mu2 = (poles && s > 0.0) ? (float)azc / (float)s : 0.f;
+            if (rvalid) pk_walk_add(pks, walk, K.nedges, s, p, wmult, mu2, poles);
+        }
+    }
+    pk_walk_flush_warp(pks, walk, poles, rvalid);
+}
+
 // ---------------------------------------------------------------------------
 // rows, inverse.  grid = ceil(na*N / RB), block = 256
 // ---------------------------------------------------------------------------
 template <int N, int SRC>
-__global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_inv(const RowsArgs A) {
+__global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsArgs A) {
     using G = RowGeom<N>;
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
@@ -174,88 +284,85 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_inv(const RowsArgs
     const size_t row_local = ((size_t)al * N + b) * N;
     const int am = (N - a) & (N - 1), bm = (N - b) & (N - 1);
     const size_t row_g = ((size_t)a * N + b) * N, row_m = ((size_t)am * N + bm) * N;
-    const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
-    const double sab = do_pk ? __dadd_rn(A.K.ax[a], A.K.ay[b]) : 0.0;
-    const bool velocity = (A.kind >= FB_KIND_VEL_X && A.kind <= FB_KIND_VEL_Z);
     const int c0 = P * t;                          // natural-order run of this thread
     const int mstart = N - c0 - P;                 // mirror block: cells mstart .. mstart+P-1  (c -> N-c)
     const int cm0 = (N - c0) & (N - 1);            // mirror of the first cell of the run
+    const bool antiherm = (A.flags & FB_F_ANTIHERM) != 0;
 
+    // ---- 1. gather: h = G(k) +/- conj G(-k)   (the factor 1/2 is folded into amp)
     float2 h[P];
     if constexpr (SRC == SRC_SPEC) {
         load_run<P>(A.src + row_local + c0, h);
     } else {
-        float2 g[P], mm[P], gm0;
+        float2 gm0;
         if constexpr (SRC == SRC_NOISE) {
-            float r[P], i[P];
+            float r[P], i[P], rm[P], im[P];
             load_run<P>(A.re + row_g + c0, r);
             load_run<P>(A.im + row_g + c0, i);
-#pragma unroll
-            for (int e = 0; e < P; ++e) g[e] = make_float2(r[e], i[e]);
-            load_run<P>(A.re + row_m + mstart, r);
-            load_run<P>(A.im + row_m + mstart, i);
-#pragma unroll
-            for (int e = 0; e < P; ++e) mm[e] = make_float2(r[e], i[e]);
+            load_run<P>(A.re + row_m + mstart, rm);
+            load_run<P>(A.im + row_m + mstart, im);
             gm0 = make_float2(__ldg(&A.re[row_m + cm0]), __ldg(&A.im[row_m + cm0]));
-        } else if constexpr (SRC == SRC_PHILOX) {
 #pragma unroll
-            for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_g + c0 + e, g[e], g[e + 1]);
+            for (int e = 0; e < P; ++e) {
+                const float2 g = make_float2(r[e], i[e]);
+                const float2 gm = (e == 0) ? gm0 : make_float2(rm[P - e], im[P - e]);
+                h[e] = antiherm ? make_float2(g.y + gm.y, gm.x - g.x) : make_float2(g.x + gm.x, g.y - gm.y);
+            }
+        } else if constexpr (SRC == SRC_PHILOX) {
+            float2 mm[P];
+#pragma unroll
+            for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_g + c0 + e, h[e], h[e + 1]);
 #pragma unroll
             for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_m + mstart + e, mm[e], mm[e + 1]);
             float2 q0, q1;
             philox_normal_quad(A.seed, (row_m + cm0) & ~(size_t)1, q0, q1);
             gm0 = ((row_m + cm0) & 1) ? q1 : q0;
+#pragma unroll
+            for (int e = 0; e < P; ++e) {
+                const float2 g = h[e];
+                const float2 gm = (e == 0) ? gm0 : mm[P - e];
+                h[e] = antiherm ? make_float2(g.y + gm.y, gm.x - g.x) : make_float2(g.x + gm.x, g.y - gm.y);
+            }
         } else {
-            load_run<P>(A.src + row_g + c0, g);
+            // full complex cube; a k_par-odd filter multiplies G(k) and G(-k) differently (box.py:378)
+            float2 mm[P];
+            load_run<P>(A.src + row_g + c0, h);
             load_run<P>(A.src + row_m + mstart, mm);
             gm0 = __ldg(&A.src[row_m + cm0]);
-        }
+            const bool filt = (A.flags & FB_F_FILTER) != 0;
 #pragma unroll
-        for (int e = 0; e < P; ++e) {
-            const float2 gm = (e == 0) ? gm0 : mm[P - e];
-            if (A.flags & FB_F_ANTIHERM)        // (G(k) - conj G(-k)) / (2i)
-                h[e] = make_float2(0.5f * (g[e].y + gm.y), -0.5f * (g[e].x - gm.x));
-            else                                // (G(k) + conj G(-k)) / 2
-                h[e] = make_float2(0.5f * (g[e].x + gm.x), 0.5f * (g[e].y - gm.y));
-            if constexpr (SRC == SRC_CUBE) {
-                // a k_par-odd filter multiplies G(k) and G(-k) differently: apply it before combining
-                if (A.flags & FB_F_FILTER) {
+            for (int e = 0; e < P; ++e) {
+                float2 g = h[e];
+                float2 gm = (e == 0) ? gm0 : mm[P - e];
+                if (filt) {
                     const int c = c0 + e, cm = (N - c) & (N - 1);
                     const float f = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, c);
                     const float fm = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, cm);
-                    const float2 x = make_float2(g[e].x * f, g[e].y * f), y = make_float2(gm.x * fm, gm.y * fm);
-                    if (A.flags & FB_F_ANTIHERM)
-                        h[e] = make_float2(0.5f * (x.y + y.y), -0.5f * (x.x - y.x));
-                    else
-                        h[e] = make_float2(0.5f * (x.x + y.x), 0.5f * (x.y - y.y));
+                    g.x *= f; g.y *= f;
+                    gm.x *= fm; gm.y *= fm;
                 }
+                h[e] = antiherm ? make_float2(g.y + gm.y, gm.x - g.x) : make_float2(g.x + gm.x, g.y - gm.y);
             }
         }
     }
-    PkWalk walk;
-    walk.bin = 0;
-    walk.cnt = 0u;
-    walk.s1 = walk.s2 = walk.l2 = walk.l4 = 0.0;
-    const int amp_flags = (SRC == SRC_CUBE) ? (A.flags & ~FB_F_FILTER) : A.flags;
+    // ---- 2. k-space multiplier
+    {
+        float amp[P];
+        const int amp_flags = (SRC == SRC_CUBE) ? (A.flags & ~FB_F_FILTER) : A.flags;
+        run_amp<N, P>(A.K, amp_flags, A.kind, a, b, c0, SRC == SRC_SPEC ? 1.f : 0.5f, amp);
+        if (A.kind >= FB_KIND_VEL_X && A.kind <= FB_KIND_VEL_Z) {          // * i, box.py:254-256
 #pragma unroll
-    for (int e = 0; e < P; ++e) {
-        const int c = c0 + e;
-        const float amp = k_amp(A.K, amp_flags, A.kind, a, b, c, c);
-        float2 v = make_float2(h[e].x * amp, h[e].y * amp);
-        if (velocity) v = make_float2(-v.y, v.x);          // * i, box.py:254-256
-        h[e] = v;
-        if (do_pk) {
-            const double azc = A.K.az[c];
-            const double s = __dadd_rn(sab, azc);
-            if (e == 0) walk.bin = pk_bin(pks, A.K.nedges, s);
-            const float p = (v.x * v.x + v.y * v.y) * (float)A.K.inv_boxfactor;
-            const float mu2 = (poles && s > 0.0) ? (float)azc / (float)s : 0.f;
-            if (rvalid) pk_walk_add(pks, walk, A.K.nedges, s, p, wmult, mu2, poles);
+            for (int e = 0; e < P; ++e) h[e] = make_float2(-h[e].y * amp[e], h[e].x * amp[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < P; ++e) h[e] = make_float2(h[e].x * amp[e], h[e].y * amp[e]);
         }
     }
     if (A.spec_out && rvalid) store_run<P>(A.spec_out + row_local + c0, h);
-    if (do_pk) pk_walk_flush_warp(pks, walk, poles, rvalid);
+    // ---- 3. binned moments of |H|^2 (box.py:741-764)
+    if (do_pk) run_pk<N, P, (T > 1)>(pks, A.K, a, b, c0, h, nullptr, poles, rvalid);
 
+    // ---- 4. natural -> Stockham order, transform c -> z, store
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
     float2 v[P];
     if constexpr (T > 1) {
@@ -280,7 +387,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_inv(const RowsArgs
 // (auto |S|^2 or cross Re S conj(X)).   grid = ceil(na*N / RB)
 // ---------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_fwd(const RowsArgs A) {
+__global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_fwd(const RowsArgs A) {
     using G = RowGeom<N>;
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
@@ -323,29 +430,13 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS) k_rows_fwd(const RowsArgs
     }
     if (A.spec_out && rvalid) store_run<P>(A.spec_out + row_local + c0, h);
     if (do_pk) {
-        const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
-        const double sab = __dadd_rn(A.K.ax[a], A.K.ay[b]);
-        PkWalk walk;
-        walk.bin = 0;
-        walk.cnt = 0u;
-        walk.s1 = walk.s2 = walk.l2 = walk.l4 = 0.0;
-        float2 x[P];
-        if (A.cross) load_run<P>(A.cross + row_local + c0, x);
-#pragma unroll
-        for (int e = 0; e < P; ++e) {
-            const int c = c0 + e;
-            const double azc = A.K.az[c];
-            const double s = __dadd_rn(sab, azc);
-            if (e == 0) walk.bin = pk_bin(pks, A.K.nedges, s);
-            float p;
-            if (A.cross)
-                p = (h[e].x * x[e].x + h[e].y * x[e].y) * (float)A.K.inv_boxfactor;
-            else
-                p = (h[e].x * h[e].x + h[e].y * h[e].y) * (float)A.K.inv_boxfactor;
-            const float mu2 = (poles && s > 0.0) ? (float)azc / (float)s : 0.f;
-            if (rvalid) pk_walk_add(pks, walk, A.K.nedges, s, p, wmult, mu2, poles);
+        if (A.cross) {
+            float2 x[P];
+            load_run<P>(A.cross + row_local + c0, x);
+            run_pk<N, P, (T > 1)>(pks, A.K, a, b, c0, h, x, poles, rvalid);
+        } else {
+            run_pk<N, P, (T > 1)>(pks, A.K, a, b, c0, h, nullptr, poles, rvalid);
         }
-        pk_walk_flush_warp(pks, walk, poles, rvalid);
         pk_shared_flush(pks, A.K, A.pk, poles);
     }
 }
