@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the FastBox field-generation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S]
+
+Metric (BASELINE.json): Mcells/s of the fused realise + anisotropic k_perp/k_par filter + binned
+P(k) pipeline.  One "step" = one full pass over one synthetic N^3 box.
+
+* N = 1 : 1024^3 (BASELINE.json configs[2] without the beam stage), white noise (re, im) float32
+  RESIDENT IN HBM when the timed region starts (28 algorithmic B/cell).
+  `value`  = device-resident throughput, CUDA events on the library stream.
+  `e2e`    = the same call through the C ABI with HOST (pinned) buffers: noise H2D and
+             field + P(k) D2H inside the timed region.
+* N > 1 : 2048^3 (configs[4]) slab-decomposed over the ranks, counter-based Philox noise,
+  one NCCL all-to-all per transform; max-over-ranks device time.
+* --impl reference : the reference's own algorithm (NumPy port of fastbox/box.py, the oracle
+  in oracle/restate.py: full complex128 numpy.fft c2c, masked per-bin loops) on the host cores,
+  on a bounded box (the reference cannot hold 1024^3: ~140 GB of float64 temporaries).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Mcells/s realise+filter+P(k)"
+BYTES_PER_CELL_HBM_NOISE = 28.0      # 8+4, 4+4, 4+4  
+BYTES_PER_CELL_PHILOX = 20.0         # 0+4, 4+4, 4+4
+PASS1_BYTES_PER_CELL = {"hbm": 12.0, "philox": 4.0}
+Z_BOX = 0.8
+NBINS = 50
+
+
+def transfer_fn(k_perp, k_par):      # reference tests/test_box.py:88-90
+    return (1. - np.exp(-0.5 * (k_par / 0.001) ** 2.)) * np.exp(-0.5 * (k_perp / 0.1) ** 2.)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.samples.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def configure_plan(plan, N, L):
+    """sqrt(P) LUT, filter tables, bins -- what CosmoBox would set up for this box."""
+    from fastbox_b200 import kspace as ks
+    from _util import pk_function
+    _, pkf = pk_function(Z_BOX)
+    bf = N ** 6. / L ** 3
+    with np.errstate(all="ignore"):
+        lut = ks.sqrt_pk_int_lut(pkf, N, L, bf)
+    ft = ks.filter_tables(transfer_fn, N, L, L, L)
+    kmin, kmax = 2. * np.pi / L, 2. * np.pi * np.sqrt(3.) * N / L
+    edges = ks.pk_bin_edges(kmin, kmax, NBINS)
+    thr = ks.bin_thresholds(edges)
+    tables = dict(lut=lut, tperp=ft.tperp, tpar=ft.tpar, thr=thr)
+    upload_tables(plan, tables)
+    return tables, edges
+
+
+def upload_tables(plan, t):
+    plan.set_sqrt_pk(t["lut"], 1)
+    plan.set_filter(t["tperp"], t["tpar"], None)
+    plan.set_pk_bins(t["thr"])
+
+
+def cpu_port_step(N, L, seed=11):
+    """One step of the reference algorithm on the CPU (oracle port): returns seconds."""
+    from oracle import restate as R
+    from _util import pk_function
+    _, pkf = pk_function(Z_BOX)
+    rng = np.random.RandomState(seed)
+    re = rng.normal(0., 1., (N, N, N))
+    im = rng.normal(0., 1., (N, N, N))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        dx, dk = R.realise_density_port(re, im, pkf, N, L, L, L)                  # box.py:161-193
+        filt = R.apply_transfer_fn_port(dk, transfer_fn, N, L, L, L)               # box.py:374-380
+        R.binned_power_spectrum_port(np.fft.fftn(filt.real), N, L, L, L, nbins=NBINS)   # box.py:736-768
+        return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_ref = 256 if (args.steps + args.warmup) <= 4 else 128
+    L = 2000.0 * n_ref / 1024.0
+    for _ in range(args.warmup):
+        cpu_port_step(n_ref, L)
+    ts = [cpu_port_step(n_ref, L) for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    val = n_ref ** 3 / t / 1e6
+    sample = ("%d^3 box per step (NumPy port of fastbox/box.py realise_density + apply_transfer_fn + "
+              "binned_power_spectrum, float64, numpy.fft is single-threaded as in the reference; the reference "
+              "cannot hold 1024^3 in host RAM)" % n_ref)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "realise+filter+P(k), %d^3 (bounded sample of the 1024^3 workload)" % n_ref,
+                       "nbins": NBINS},
+            "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_single(args):
+    import torch
+    from fastbox_b200 import _lib
+    N = args.size
+    L = 2000.0 * N / 1024.0
+    dev = 0
+    torch.cuda.set_device(dev)
+    plan = _lib.Plan(N, L, L, L, dev)
+    tables, edges = configure_plan(plan, N, L)
+    hbm_peak, peak_src = measured_peaks()
+    n3 = N ** 3
+    flags = _lib.F_SQRTPK | _lib.F_FILTER
+    # synthetic white noise, resident in HBM (torch is only the tensor carrier)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    re = torch.randn(n3, device="cuda", dtype=torch.float32, generator=g)
+    im = torch.randn(n3, device="cuda", dtype=torch.float32, generator=g)
+    field = torch.empty(n3, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+
+    def step_dev():
+        return plan.realise(re, im, flags=flags, field_out=field, want_pk=True)
+
+    for _ in range(args.warmup):
+        step_dev()
+    pass_ms = np.zeros(3)
+    launches0 = _lib.launch_count()
+    with ClockSampler(dev) as clk:
+        plan.sync()
+        plan.timer_start()
+        for _ in range(args.steps):
+            res, sums = step_dev()
+            pass_ms += np.array(plan.last_timings(3))
+        ms = plan.timer_stop()
+    launches = _lib.launch_count() - launches0
+    ms_step = ms / args.steps
+    pass_ms /= args.steps
+    value = n3 / (ms_step * 1e-3) / 1e6
+
+    # Philox variant (no noise read), same pipeline
+    for _ in range(2):
+        plan.realise(None, None, seed=1, flags=flags, field_out=field, want_pk=True)
+    plan.sync()
+    plan.timer_start()
+    for it in range(max(2, args.steps // 2)):
+        plan.realise(None, None, seed=it, flags=flags, field_out=field, want_pk=True)
+    ms_philox = plan.timer_stop() / max(2, args.steps // 2)
+
+    # ---- e2e: host (pinned) buffers through the same C-ABI call
+    e2e = None
+    try:
+        h_re = plan.host_alloc((n3,), np.float32)
+        h_im = plan.host_alloc((n3,), np.float32)
+        h_field = plan.host_alloc((n3,), np.float32)
+        _lib.check(plan.lib.fb_copy(plan.h, h_re.ctypes.data, re.data_ptr(), n3 * 4))
+        _lib.check(plan.lib.fb_copy(plan.h, h_im.ctypes.data, im.data_ptr(), n3 * 4))
+        e2e_steps = max(2, min(args.steps, 5))
+        plan.realise(h_re, h_im, flags=flags, field_out=h_field, want_pk=True)       # warm staging buffers
+        plan.sync()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            upload_tables(plan, tables)
+            res_h, _ = plan.realise(h_re, h_im, flags=flags, field_out=h_field, want_pk=True)
+        plan.sync()
+        t_e2e = (time.perf_counter() - t0) / e2e_steps
+        tab_bytes = int(sum(np.asarray(v).nbytes for v in tables.values()))
+        e2e = {"value": n3 / t_e2e / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 2 * 4 * n3 + tab_bytes,
+               "d2h_bytes_per_step": 4 * n3 + 3 * 8 * (NBINS + 1), "ms_per_step": t_e2e * 1e3,
+               "api": "fb_realise(host re, host im -> host field, P(k) moments) via ctypes"}
+    except Exception as exc:      # pragma: no cover
+        e2e = {"value": None, "unit": "Mcells/s", "error": str(exc)}
+
+    # ---- roofline of the dominant kernel (longest pass) and of the whole step
+    names = ["k_rows_inv (noise -> Hermitian spectrum, sqrtP, filter, P(k), z FFT)", "k_cols_c2c (y FFT)",
+             "k_x_c2r (x FFT, half-complex -> real)"]
+    nh = (N // 2 + 1) * N * N                                   # half-spectrum points (complex64)
+    pass_bytes = [8.0 * n3 + 8.0 * nh, 16.0 * nh, 8.0 * nh + 4.0 * n3]     # 8+4, 4+4, 4+4 B/cell
+    dom = int(np.argmax(pass_ms))
+    ach = pass_bytes[dom] / (pass_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "pipeline": {"bytes_per_cell": BYTES_PER_CELL_HBM_NOISE,
+                             "achieved": BYTES_PER_CELL_HBM_NOISE * n3 / (ms_step * 1e-3) / 1e9,
+                             "frac": BYTES_PER_CELL_HBM_NOISE * n3 / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                             "frac_nominal_8TBs": BYTES_PER_CELL_HBM_NOISE * n3 / (ms_step * 1e-3) / 1e9 / 8000.0,
+                             "strict_io_floor_frac": 12.0 * n3 / (ms_step * 1e-3) / 1e9 / hbm_peak},
+                "pass_ms": [float(x) for x in pass_ms],
+                "philox_variant": {"ms_per_step": ms_philox, "Mcells_per_s": n3 / (ms_philox * 1e-3) / 1e6,
+                                   "frac": BYTES_PER_CELL_PHILOX * n3 / (ms_philox * 1e-3) / 1e9 / hbm_peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(["rows_inv", "cols", "x_c2r"][dom])
+        except Exception:
+            pass
+
+    # ---- CPU baseline (oracle port) on a bounded sample
+    cpu = None
+    if not args.no_cpu:
+        n_cpu = args.cpu_size
+        t_cpu = cpu_port_step(n_cpu, 2000.0 * n_cpu / 1024.0)
+        cpu = {"value": n_cpu ** 3 / t_cpu / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
+               "sample": "one %d^3 box (%.1f s): NumPy port of fastbox/box.py realise_density + apply_transfer_fn + "
+                         "binned_power_spectrum, float64; numpy.fft is single-threaded as shipped; host has %d cores"
+                         % (n_cpu, t_cpu, os.cpu_count() or 0)}
+
+    line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d^3 realise + k_perp/k_par filter + binned P(k) (nbins=%d), white noise "
+                                   "resident in HBM" % (N, NBINS),
+                       "box_Mpc": L, "redshift": Z_BOX,
+                       "l2": "inputs (%.1f GB noise) larger than L2 (126 MB); no flush needed" % (8 * n3 / 1e9)},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    plan.close()
+
+
+def run_multi(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from fastbox_b200 import _lib
+    from fastbox_b200 import dist as fbd
+    N = args.size_multi
+    L = 2000.0 * N / 1024.0
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    eng = fbd.CudaEngine(N, (L, L, L), rank, world, local_rank)
+    configure_plan(eng.plan, N, L)
+    dr = fbd.DistributedRealiser(eng)
+    flags = _lib.F_SQRTPK | _lib.F_FILTER
+
+    def step(seed):
+        return dr.realise(seed, flags, want_pk=True)
+
+    for w in range(args.warmup):
+        step(w)
+    launches0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        # the library stream is host-synchronised around every hand-over to torch's stream, so
+        # events on torch's stream bracket all device work of the steps
+        ev0.record()
+        for s in range(args.steps):
+            eng.realise_kspace(s, flags, True)
+            eng.sync()
+            xev[s][0].record()
+            dr.exchange()
+            xev[s][1].record()
+            eng.sync_exchange()
+            eng.x_to_real()
+            eng.sync()
+        ev1.record()
+        torch.cuda.synchronize()
+    t_wall = ev0.elapsed_time(ev1) * 1e-3
+    t_x = sum(a.elapsed_time(b) for a, b in xev) * 1e-3
+    dist.barrier()
+    t = torch.tensor([t_wall, t_x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_wall, t_x = float(t[0]), float(t[1])
+    launches = _lib.launch_count() - launches0
+    if rank == 0:
+        ms_step = t_wall / args.steps * 1e3
+        value = N ** 3 / (ms_step * 1e-3) / 1e6
+        hbm_peak, peak_src = measured_peaks()
+        a2a = max(fbd.alltoall_bytes_per_rank(N, world))
+        nv = a2a / (t_x / args.steps) / 1e9 if t_x > 0 else None
+        line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "%d^3 realise + filter + binned P(k), Philox noise, slab decomposition over "
+                                       "%d GPUs, one NCCL all-to-all" % (N, world), "box_Mpc": L,
+                           "l2": "per-GPU working set %.1f GB >> L2" % (12.0 * N ** 3 / world / 1e9)},
+                "clocks": clk.summary(), "gpu_launches": int(launches),
+                "e2e": {"value": value, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step":
+                        3 * 8 * (NBINS + 1), "note": "Philox noise is generated on the device; the P(k) moments are "
+                        "read back every step; the field stays sharded on the GPUs"},
+                "roofline": {"bound": "hbm", "achieved": BYTES_PER_CELL_PHILOX * N ** 3 / world / (ms_step * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": BYTES_PER_CELL_PHILOX * N ** 3 / world / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                             "traffic": None, "peak_source": peak_src,
+                             "nvlink": {"bytes_sent_per_gpu": a2a, "exchange_ms": t_x / args.steps * 1e3,
+                                        "achieved_GBs": nv, "frac_of_900": None if nv is None else nv / 900.0,
+                                        "frac_of_measured_770": None if nv is None else nv / 770.0}},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="grid size for the single-GPU run")
+    ap.add_argument("--size-multi", type=int, default=2048, help="grid size for the multi-GPU run")
+    ap.add_argument("--cpu-size", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        run_multi(args, rank, world, local_rank)
+    else:
+        run_single(args)
+
+
+if __name__ == "__main__":
+    main()

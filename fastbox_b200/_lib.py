@@ -64,7 +64,8 @@ SIGNATURES = {
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_r2c": (_i, [_vp, _vp, _vp, _l]),
-    "fb_realise_local_kspace": (_i, [_vp, _u64, _i, _vp, C.POINTER(PkResult)]),
+    "fb_realise_local_kspace": (_i, [_vp, _u64, _i, _vp, _vp, _i, C.POINTER(PkResult)]),
+    "fb_forward_local_kspace": (_i, [_vp, _vp, _vp, _i, _vp, _i, C.POINTER(PkResult)]),
     "fb_bench_strided_copy": (_i, [_vp, _sz, _i, _i, C.POINTER(_d)]),
     "fb_last_timings": (_i, [_vp, C.POINTER(_f), _i]),
     "fb_timer_start": (_i, [_vp]),
@@ -301,10 +302,16 @@ class Plan(object):
     def fft_pass_x_r2c(self, field, spec, ncols):
         check(self.lib.fb_fft_pass_x_r2c(self.h, _ptr(field), _ptr(spec), int(ncols)))
 
-    def realise_local_kspace(self, seed, flags, work, want_pk=False):
+    def realise_local_kspace(self, seed, flags, work, send=None, ny=0, want_pk=False):
         st, res = (self._pk_struct(False) if want_pk else (None, None))
-        check(self.lib.fb_realise_local_kspace(self.h, int(seed), int(flags), _ptr(work),
+        check(self.lib.fb_realise_local_kspace(self.h, int(seed), int(flags), _ptr(work), _ptr(send), int(ny),
                                                C.byref(st) if st is not None else None))
+        return res
+
+    def forward_local_kspace(self, recv, work, ny, spec_out=None, want_pk=False, poles=False):
+        st, res = (self._pk_struct(poles) if want_pk else (None, None))
+        check(self.lib.fb_forward_local_kspace(self.h, _ptr(recv), _ptr(work), int(ny), _ptr(spec_out),
+                                               F_POLES if poles else 0, C.byref(st) if st is not None else None))
         return res
 
     def bench_strided_copy(self, total_bytes, chunk_bytes, iters=5):

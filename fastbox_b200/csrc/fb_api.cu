@@ -616,9 +616,11 @@ int fb_fft_pass_x_r2c(fb_plan* p, const float* field, void* spec, long ncols) {
     return launch_x_r2c(p, xa);
 }
 
-int fb_realise_local_kspace(fb_plan* p, uint64_t seed, int flags, void* work, fb_pk_result* pk) {
+int fb_realise_local_kspace(fb_plan* p, uint64_t seed, int flags, void* work, void* send, int ny, fb_pk_result* pk) {
     FB_CUDA(cudaSetDevice(p->device));
     FB_CHECK(is_device_ptr(work), "fb_realise_local_kspace: work must be device memory");
+    FB_CHECK(ny == 0 || (send != nullptr && is_device_ptr(send) && send != work && p->N % ny == 0),
+             "fb_realise_local_kspace: ny must divide N and send must be a distinct device buffer");
     if (pk) flags |= FB_F_PK; else flags &= ~(FB_F_PK | FB_F_POLES);
     if (check_flags(p, flags)) return -1;
     RowsArgs ra;
@@ -632,8 +634,45 @@ int fb_realise_local_kspace(fb_plan* p, uint64_t seed, int flags, void* work, fb
     ra.K = p->kspace();
     ra.pk = p->pkdev();
     if (pk && pk_clear(p)) return -2;
+    mark(p, 0);
     if (launch_rows_inv_philox(p, ra)) return -3;
-    if (launch_cols(p, (float2*)work, p->na, +1)) return -3;
+    mark(p, 1);
+    if (ny == 0) {
+        if (launch_cols(p, (float2*)work, p->na, +1)) return -3;
+    } else {
+        if (launch_cols_ex(p, (const float2*)work, (float2*)send, 0, ny, p->na, +1)) return -3;
+    }
+    mark(p, 2);
+    p->n_last = 2;
+    if (pk && pk_fetch(p, pk)) return -2;
+    return 0;
+}
+
+int fb_forward_local_kspace(fb_plan* p, const void* recv, void* work, int ny, void* spec_out, int flags,
+                            fb_pk_result* pk) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(is_device_ptr(recv) && is_device_ptr(work) && recv != work, "fb_forward_local_kspace: need two device buffers");
+    FB_CHECK(ny > 0 && p->N % ny == 0, "fb_forward_local_kspace: ny must divide N");
+    FB_CHECK(spec_out == nullptr || is_device_ptr(spec_out), "fb_forward_local_kspace: spec_out must be device memory");
+    if (pk) flags |= FB_F_PK; else flags &= ~(FB_F_PK | FB_F_POLES);
+    flags &= (FB_F_PK | FB_F_POLES);
+    if (check_flags(p, flags)) return -1;
+    if (pk && pk_clear(p)) return -2;
+    mark(p, 0);
+    if (launch_cols_ex(p, (const float2*)recv, (float2*)work, ny, 0, p->na, -1)) return -3;
+    mark(p, 1);
+    RowsArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.work = (float2*)work;
+    ra.spec_out = (float2*)spec_out;
+    ra.tw = p->tw;
+    ra.nrows = (long)p->na * p->N;
+    ra.flags = flags;
+    ra.K = p->kspace();
+    ra.pk = p->pkdev();
+    if (launch_rows_fwd(p, ra)) return -3;
+    mark(p, 2);
+    p->n_last = 2;
     if (pk && pk_fetch(p, pk)) return -2;
     return 0;
 }

@@ -10,17 +10,17 @@ int env_int(const char* name, int dflt) {
 }
 
 template <int N, int CZ>
-static int launch_cols_t(fb_plan* p, float2* data, int nplanes, int sign) {
+static int launch_cols_t(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign) {
     using G = ColGeom<N, CZ>;
     dim3 grid(N / CZ, nplanes);
     if (sign < 0) {
         auto kern = k_cols_c2c<N, CZ, -1>;
         if (set_smem(kern, G::SMEM)) return -2;
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(data, p->tw);
+        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(in, out, in_ny, out_ny, p->tw);
     } else {
         auto kern = k_cols_c2c<N, CZ, +1>;
         if (set_smem(kern, G::SMEM)) return -2;
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(data, p->tw);
+        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(in, out, in_ny, out_ny, p->tw);
     }
     FB_LAUNCH_CHECK();
     return 0;
@@ -30,28 +30,30 @@ static int launch_cols_t(fb_plan* p, float2* data, int nplanes, int sign) {
 // chunks (tools/probe.py), so narrow tiles are preferred: more CTAs per SM overlap load /
 // exchange / store phases.  FB_CZ_COLS / FB_CZ_X override for tuning.
 template <int N>
-static int launch_cols_n(fb_plan* p, float2* data, int nplanes, int sign, int dflt) {
+static int launch_cols_n(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign, int dflt) {
     const int cz = env_int("FB_CZ_COLS", dflt);
-    if (cz == 4) return launch_cols_t<N, 4>(p, data, nplanes, sign);
-    if (cz == 8) return launch_cols_t<N, 8>(p, data, nplanes, sign);
+    if (cz == 4) return launch_cols_t<N, 4>(p, in, out, in_ny, out_ny, nplanes, sign);
+    if (cz == 8) return launch_cols_t<N, 8>(p, in, out, in_ny, out_ny, nplanes, sign);
     if constexpr (N <= 1024) {
-        if (cz == 16) return launch_cols_t<N, 16>(p, data, nplanes, sign);
+        if (cz == 16) return launch_cols_t<N, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
     }
     set_error("FB_CZ_COLS=%d not available for N=%d", cz, N);
     return -1;
 }
 
-int launch_cols(fb_plan* p, float2* data, int nplanes, int sign) {
+int launch_cols(fb_plan* p, float2* data, int nplanes, int sign) { return launch_cols_ex(p, data, data, 0, 0, nplanes, sign); }
+
+int launch_cols_ex(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign) {
     switch (p->N) {
-        case 8: return launch_cols_t<8, 8>(p, data, nplanes, sign);
-        case 16: return launch_cols_t<16, 16>(p, data, nplanes, sign);
-        case 32: return launch_cols_t<32, 16>(p, data, nplanes, sign);
-        case 64: return launch_cols_t<64, 16>(p, data, nplanes, sign);
-        case 128: return launch_cols_t<128, 16>(p, data, nplanes, sign);
-        case 256: return launch_cols_n<256>(p, data, nplanes, sign, 16);
-        case 512: return launch_cols_n<512>(p, data, nplanes, sign, 8);
-        case 1024: return launch_cols_n<1024>(p, data, nplanes, sign, 8);
-        case 2048: return launch_cols_n<2048>(p, data, nplanes, sign, 4);
+        case 8: return launch_cols_t<8, 8>(p, in, out, in_ny, out_ny, nplanes, sign);
+        case 16: return launch_cols_t<16, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
+        case 32: return launch_cols_t<32, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
+        case 64: return launch_cols_t<64, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
+        case 128: return launch_cols_t<128, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
+        case 256: return launch_cols_n<256>(p, in, out, in_ny, out_ny, nplanes, sign, 16);
+        case 512: return launch_cols_n<512>(p, in, out, in_ny, out_ny, nplanes, sign, 8);
+        case 1024: return launch_cols_n<1024>(p, in, out, in_ny, out_ny, nplanes, sign, 8);
+        case 2048: return launch_cols_n<2048>(p, in, out, in_ny, out_ny, nplanes, sign, 4);
         default: set_error("unsupported N=%d", p->N); return -1;
     }
 }

@@ -11,6 +11,7 @@ int launch_rows_inv_cube(fb_plan* p, const RowsArgs& a);
 int launch_rows_fwd(fb_plan* p, const RowsArgs& a);
 int launch_pk_spectrum(fb_plan* p, const float2* spec, const float2* cross, int nplanes, int full_cube, int flags);
 int launch_cols(fb_plan* p, float2* data, int nplanes, int sign);
+int launch_cols_ex(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign);
 int launch_x_c2r(fb_plan* p, const XArgs& a);
 int launch_x_r2c(fb_plan* p, const XArgs& a);
 

@@ -452,22 +452,34 @@ struct ColGeom {
     static constexpr size_t SMEM = (size_t)(N + N / 16) * CZ * sizeof(float2);
 };
 
+// Slab-decomposed runs exchange the y axis between ranks right after (inverse) / before
+// (forward) this pass.  With ny > 0 the y index is split as y = d*ny + y' and the element lives
+// at [d][plane][y'][z]: the block for destination rank d is contiguous, so the all-to-all needs
+// no pack / unpack pass over HBM.  ny = 0 is the plain [plane][y][z] layout.
+__device__ __forceinline__ size_t col_index(int plane, int nplanes, int y, int ny, int N) {
+    if (ny == 0) return ((size_t)plane * N + y) * N;
+    const int d = y / ny, yy = y - d * ny;
+    return (((size_t)d * nplanes + plane) * ny + yy) * N;
+}
+
 template <int N, int CZ, int S>
-__global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(float2* __restrict__ data,
+__global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const float2* __restrict__ in,
+                                                                     float2* __restrict__ out, int in_ny, int out_ny,
                                                                      const float2* __restrict__ tw) {
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
-    float2* base = data + (size_t)blockIdx.y * N * N + (size_t)blockIdx.x * CZ + col;
+    const int plane = blockIdx.y, nplanes = gridDim.y;
+    const size_t zc = (size_t)blockIdx.x * CZ + col;
     float2 v[P];
 #pragma unroll
-    for (int q = 0; q < P; ++q) v[q] = base[(size_t)(t + T * q) * N];
+    for (int q = 0; q < P; ++q) v[q] = in[col_index(plane, nplanes, t + T * q, in_ny, N) + zc];
     ColLayout<CZ> sl{col};
     fft_regs<N, P, C::R1, C::R2, C::R3, S>(v, t, sm, sl, tw);
 #pragma unroll
-    for (int q = 0; q < P; ++q) base[(size_t)(t + T * q) * N] = v[q];
+    for (int q = 0; q < P; ++q) out[col_index(plane, nplanes, t + T * q, out_ny, N) + zc] = v[q];
 }
 
 // ---------------------------------------------------------------------------

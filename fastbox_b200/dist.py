@@ -1,0 +1,131 @@
+"""
+Slab-decomposed (multi-GPU) realise / P(k) pipelines: one process per GPU,
+``torch.distributed`` (NCCL over NVLink) for the single exchange step of each 3-D FFT.
+
+Decomposition (DESIGN.md section "Multi-GPU"):
+
+* spectrum side: the kx planes a = 0..N/2 are split over the P ranks (N/(2P) planes each,
+  the last rank also owns the Nyquist plane a = N/2); the z (rows) and y (columns) passes are
+  local;
+* real side: y rows are split over the ranks (N/P each); the x pass is local.
+
+Between the two sits ONE all-to-all of the half spectrum per transform.  The y pass writes its
+output already grouped by destination rank (``[dest][plane][y'][z]``) and the receive buffer of
+``all_to_all_single`` is exactly the ``[kx][y'][z]`` array the x pass consumes, so no pack/unpack
+kernels are needed.  P(k) moments are per-rank partial histograms summed with ``all_reduce``.
+
+The reference (``fastbox/box.py``) is single process; this module has no counterpart there.
+
+The local compute is behind ``engine`` so that the exchange bookkeeping can be exercised on
+CPU (gloo) with a NumPy engine in ``tests/test_dist_gloo.py``; the product engine is
+``CudaEngine`` (C ABI, no CPU fallback).
+"""
+import numpy as np
+
+from . import _lib
+
+
+def slab_geometry(N, world, rank):
+    """(a0, na, y0, ny): local kx planes [a0, a0+na) and local y rows [y0, y0+ny)."""
+    if world < 1 or (N // 2) % world != 0 or N % world != 0:
+        raise ValueError("world size %d must divide N/2 = %d" % (world, N // 2))
+    per = (N // 2) // world
+    a0 = rank * per
+    na = per + (1 if rank == world - 1 else 0)
+    ny = N // world
+    return a0, na, rank * ny, ny
+
+
+def plane_counts(N, world):
+    return [slab_geometry(N, world, r)[1] for r in range(world)]
+
+
+def alltoall_bytes_per_rank(N, world):
+    """Bytes each rank sends (= receives) per transform, excluding its own block."""
+    ny = N // world
+    return [8 * na * ny * N * (world - 1) for na in plane_counts(N, world)]
+
+
+class CudaEngine(object):
+    """Local passes on one GPU through libfastbox_b200 (torch tensors carry the buffers)."""
+
+    def __init__(self, N, L, rank, world, device):
+        import torch
+        self.torch = torch
+        self.N, self.rank, self.world = N, rank, world
+        self.a0, self.na, self.y0, self.ny = slab_geometry(N, world, rank)
+        self.dev = torch.device("cuda", device)
+        self.plan = _lib.Plan(N, L[0], L[1], L[2], device)
+        self.plan.set_slab(self.a0, self.na, self.y0, self.ny)
+        c64 = torch.complex64
+        self.work = torch.empty((self.na, N, N), dtype=c64, device=self.dev)
+        self.send = torch.empty((world, self.na, self.ny, N), dtype=c64, device=self.dev)
+        self.recv = torch.empty((N // 2 + 1, self.ny, N), dtype=c64, device=self.dev)
+        self.field = torch.empty((N, self.ny, N), dtype=torch.float32, device=self.dev)
+
+    def realise_kspace(self, seed, flags, want_pk):
+        """rows + columns on the local planes; fills ``self.send``; returns local P(k) moments."""
+        return self.plan.realise_local_kspace(seed, flags, self.work, self.send, self.ny, want_pk=want_pk)
+
+    def x_to_real(self, flags=0, scale=1.0):
+        N = self.N
+        return self.plan.fft_pass_x_c2r(self.recv, self.field, self.ny * N, flags=flags,
+                                        scale=scale / float(N) ** 3)
+
+    def sync(self):
+        self.plan.sync()
+
+    def sync_exchange(self):
+        """NCCL runs on torch's current stream: wait for it before the x pass (plan stream)."""
+        self.torch.cuda.current_stream(self.dev).synchronize()
+
+    def moments_tensor(self, res):
+        t = self.torch
+        n = self.plan.nedges + 1
+        arr = np.concatenate([res["count"][:n].astype(np.float64), res["sum1"][:n], res["sum2"][:n]])
+        return t.from_numpy(arr).to(self.dev)
+
+
+class DistributedRealiser(object):
+    """Realise (+ filter + P(k)) a Gaussian field on an N^3 grid sharded over the ranks."""
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.e = engine
+        self.group = group
+        N, world = engine.N, engine.world
+        ny = engine.ny
+        self.in_splits = [engine.na * ny * N] * world                 # elements sent to each peer
+        self.out_splits = [na * ny * N for na in plane_counts(N, world)]
+
+    def exchange(self):
+        e = self.e
+        if e.world == 1:
+            e.recv.reshape(-1).copy_(e.send.reshape(-1))
+            return
+        self.dist.all_to_all_single(e.recv.reshape(-1), e.send.reshape(-1),
+                                    output_split_sizes=self.out_splits, input_split_sizes=self.in_splits,
+                                    group=self.group)
+
+    def realise(self, seed, flags, want_pk=False, scale=1.0):
+        """
+        Returns (local field slab handle, global P(k) moments or None).  The y pass and the
+        exchange are ordered on the device: the plan stream is synchronised before NCCL runs
+        on torch's stream, and torch's stream before the x pass.
+        """
+        e = self.e
+        res = e.realise_kspace(seed, flags, want_pk)
+        e.sync()
+        self.exchange()
+        e.sync_exchange()
+        sums = e.x_to_real(flags=flags & _lib.F_EXP, scale=scale)
+        pk = None
+        if want_pk:
+            t = e.moments_tensor(res)
+            if e.world > 1:
+                self.dist.all_reduce(t, group=self.group)
+            arr = t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+            n = arr.size // 3
+            pk = dict(count=np.rint(arr[:n]).astype(np.uint64), sum1=arr[n:2 * n], sum2=arr[2 * n:])
+        return e.field, pk, sums

@@ -166,9 +166,16 @@ int fb_fft_pass_c2c(fb_plan* plan, void* data, int nplanes, int pass, int sign);
 int fb_fft_pass_x_c2r(fb_plan* plan, const void* spec, float* field, long ncols, int flags, float scale,
                       double* sum_out);
 int fb_fft_pass_x_r2c(fb_plan* plan, const float* field, void* spec, long ncols);
-/* first pass of realise on the local slab only (rows z + y columns), result in
- * `work` [na][N][N]; and last passes of the forward transform.                 */
-int fb_realise_local_kspace(fb_plan* plan, uint64_t seed, int flags, void* work, fb_pk_result* pk);
+/* Slab-decomposed (multi-GPU) halves of the pipelines; the all-to-all between them is done by
+ * the caller (torch.distributed / NCCL, fastbox_b200/dist.py).  `ny` = y rows per rank.
+ * realise: Philox noise -> Hermitian spectrum on the local kx planes -> z rows, y columns;
+ * the result is written to `send` as [dest rank][local plane][ny][N] (contiguous per peer).  */
+int fb_realise_local_kspace(fb_plan* plan, uint64_t seed, int flags, void* work, void* send, int ny,
+                            fb_pk_result* pk);
+/* forward: `recv` = [src rank -> local plane... ] i.e. [d][local plane][ny][N] as received;
+ * y columns + z rows on the local kx planes, optional spectrum store and binned moments.      */
+int fb_forward_local_kspace(fb_plan* plan, const void* recv, void* work, int ny, void* spec_out, int flags,
+                            fb_pk_result* pk);
 /* strided HBM copy micro-benchmark: rows of `chunk_bytes`, returns GB/s        */
 int fb_bench_strided_copy(fb_plan* plan, size_t total_bytes, int chunk_bytes, int iters, double* gbs);
 /* CUDA-event stopwatch on the plan's stream (bench.py times the step loop with it) */
