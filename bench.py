@@ -110,18 +110,18 @@ def configure_plan(plan, N, L):
     _, pkf = pk_function(Z_BOX)
     bf = N ** 6. / L ** 3
     with np.errstate(all="ignore"):
-        lut = ks.sqrt_pk_int_lut(pkf, N, L, bf)
+        mode, lut, l0, dl = ks.choose_sqrt_pk_table(pkf, N, L, L, L, bf)
     ft = ks.filter_tables(transfer_fn, N, L, L, L)
     kmin, kmax = 2. * np.pi / L, 2. * np.pi * np.sqrt(3.) * N / L
     edges = ks.pk_bin_edges(kmin, kmax, NBINS)
     thr = ks.bin_thresholds(edges)
-    tables = dict(lut=lut, tperp=ft.tperp, tpar=ft.tpar, thr=thr)
+    tables = dict(lut=lut, tperp=ft.tperp, tpar=ft.tpar, thr=thr, lut_mode=(mode, l0, dl))
     upload_tables(plan, tables)
     return tables, edges
 
 
 def upload_tables(plan, t):
-    plan.set_sqrt_pk(t["lut"], 1)
+    plan.set_sqrt_pk(t["lut"], *t["lut_mode"])
     plan.set_filter(t["tperp"], t["tpar"], None)
     plan.set_pk_bins(t["thr"])
 
@@ -233,7 +233,7 @@ def run_single(args):
             res_h, _ = plan.realise(h_re, h_im, flags=flags, field_out=h_field, want_pk=True)
         plan.sync()
         t_e2e = (time.perf_counter() - t0) / e2e_steps
-        tab_bytes = int(sum(np.asarray(v).nbytes for v in tables.values()))
+        tab_bytes = int(sum(np.asarray(v).nbytes for k, v in tables.items() if k != "lut_mode"))
         e2e = {"value": n3 / t_e2e / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 2 * 4 * n3 + tab_bytes,
                "d2h_bytes_per_step": 4 * n3 + 3 * 8 * (NBINS + 1), "ms_per_step": t_e2e * 1e3,
                "api": "fb_realise(host re, host im -> host field, P(k) moments) via ctypes"}

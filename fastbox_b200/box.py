@@ -218,11 +218,8 @@ class CosmoBox(object):
         fn = ccl.linear_matter_power if linear else ccl.nonlin_matter_power
         pk = lambda kk: fn(self.cosmo, k=kk, a=scale_factor)                     # box.py:162-165
         with np.errstate(all="ignore"):
-            if self.cubic:
-                self._plan.set_sqrt_pk(ks.sqrt_pk_int_lut(pk, self.N, self.Lx, self.boxfactor), 1)
-            else:
-                tab, l0, dl = ks.sqrt_pk_log_table(pk, self.N, self.Lx, self.Ly, self.Lz, self.boxfactor)
-                self._plan.set_sqrt_pk(tab, 2, l0, dl)
+            mode, tab, l0, dl = ks.choose_sqrt_pk_table(pk, self.N, self.Lx, self.Ly, self.Lz, self.boxfactor)
+        self._plan.set_sqrt_pk(tab, mode, l0, dl)
         self._pk_key = key
 
     def _load_isotropic(self, fn_of_k):
@@ -234,8 +231,8 @@ class CosmoBox(object):
                 kk = 2. * np.pi * np.sqrt(n) / self.Lx
                 self._plan.set_sqrt_pk(np.nan_to_num(fn_of_k(kk)).astype(np.float32), 1)
             else:
-                tab, l0, dl = ks.sqrt_pk_log_table(lambda kk: np.nan_to_num(fn_of_k(kk)) ** 2., self.N, self.Lx,
-                                                   self.Ly, self.Lz, 1.0)
+                s, l0, dl = ks.log_table_nodes(self.N, self.Lx, self.Ly, self.Lz, 1 << 16)
+                tab = np.nan_to_num(fn_of_k(2. * np.pi * np.sqrt(s))).astype(np.float32)
                 self._plan.set_sqrt_pk(tab, 2, l0, dl)
 
     def _load_bins(self, nbins, kbins):

@@ -97,20 +97,35 @@ int ensure_aux(fb_plan* p, size_t bytes) {
 }
 
 int pk_clear(fb_plan* p) {
-    FB_CUDA(cudaMemsetAsync(p->h_count, 0, (FB_MAX_EDGES + 1) * sizeof(unsigned long long), p->stream));
-    FB_CUDA(cudaMemsetAsync(p->h_sums, 0, 4 * (FB_MAX_EDGES + 1) * sizeof(double), p->stream));
+    FB_CUDA(cudaMemsetAsync(p->h_count, 0, FB_PK_COPIES * (FB_MAX_EDGES + 1) * sizeof(unsigned long long), p->stream));
+    FB_CUDA(cudaMemsetAsync(p->h_sums, 0, 4 * FB_PK_COPIES * (FB_MAX_EDGES + 1) * sizeof(double), p->stream));
     return 0;
 }
 
 int pk_fetch(fb_plan* p, fb_pk_result* out) {
     const int n = p->nedges + 1;
     FB_CUDA(cudaStreamSynchronize(p->stream));
-    if (out->count) FB_CUDA(cudaMemcpy(out->count, p->h_count, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    // the device histogram is replicated FB_PK_COPIES times (CTAs spread their reductions over
+    // the copies so that no single L2 address serialises them); sum the copies here
+    const size_t per = (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
+    std::vector<unsigned long long> hc(per);
+    std::vector<double> hs(4 * per);
+    FB_CUDA(cudaMemcpy(hc.data(), p->h_count, per * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    FB_CUDA(cudaMemcpy(hs.data(), p->h_sums, 4 * per * sizeof(double), cudaMemcpyDeviceToHost));
     double* dst[4] = {out->sum1, out->sum2, out->sum_l2, out->sum_l4};
-    for (int i = 0; i < 4; ++i)
-        if (dst[i])
-            FB_CUDA(cudaMemcpy(dst[i], p->h_sums + (size_t)i * (FB_MAX_EDGES + 1), n * sizeof(double),
-                               cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        if (out->count) {
+            unsigned long long c = 0;
+            for (int k = 0; k < FB_PK_COPIES; ++k) c += hc[(size_t)k * (FB_MAX_EDGES + 1) + i];
+            out->count[i] = c;
+        }
+        for (int j = 0; j < 4; ++j)
+            if (dst[j]) {
+                double s = 0.0;
+                for (int k = 0; k < FB_PK_COPIES; ++k) s += hs[(size_t)j * per + (size_t)k * (FB_MAX_EDGES + 1) + i];
+                dst[j][i] = s;
+            }
+    }
     return 0;
 }
 
@@ -153,6 +168,8 @@ fb::KSpace fb_plan::kspace() const {
     K.az = az;
     K.thr = thr;
     K.nedges = nedges;
+    K.bin_l0 = (float)bin_l0;
+    K.bin_inv_d = (float)bin_inv_d;
     K.inv_boxfactor = (Lx * Ly * Lz) / pow((double)N, 6.0);        // 1 / box.py:94
     return K;
 }
@@ -161,9 +178,9 @@ fb::PkDev fb_plan::pkdev() const {
     fb::PkDev d;
     d.count = h_count;
     d.sum1 = h_sums;
-    d.sum2 = h_sums + (FB_MAX_EDGES + 1);
-    d.l2 = h_sums + 2 * (FB_MAX_EDGES + 1);
-    d.l4 = h_sums + 3 * (FB_MAX_EDGES + 1);
+    d.sum2 = h_sums + (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
+    d.l2 = h_sums + 2 * (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
+    d.l4 = h_sums + 3 * (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
     return d;
 }
 
@@ -228,8 +245,8 @@ int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int de
         p->az = p->ax + 2 * (size_t)N;
     }
     FB_CUDA(cudaMalloc((void**)&p->thr, FB_MAX_EDGES * sizeof(double)));
-    FB_CUDA(cudaMalloc((void**)&p->h_count, (FB_MAX_EDGES + 1) * sizeof(unsigned long long)));
-    FB_CUDA(cudaMalloc((void**)&p->h_sums, 4 * (FB_MAX_EDGES + 1) * sizeof(double)));
+    FB_CUDA(cudaMalloc((void**)&p->h_count, FB_PK_COPIES * (FB_MAX_EDGES + 1) * sizeof(unsigned long long)));
+    FB_CUDA(cudaMalloc((void**)&p->h_sums, 4 * FB_PK_COPIES * (FB_MAX_EDGES + 1) * sizeof(double)));
     FB_CUDA(cudaMalloc((void**)&p->scal, 8 * sizeof(double)));
     FB_CUDA(cudaMallocHost((void**)&p->scal_host, 8 * sizeof(double)));
     for (int i = 0; i < 8; ++i) FB_CUDA(cudaEventCreate(&p->ev[i]));
@@ -355,6 +372,18 @@ int fb_set_pk_bins(fb_plan* p, const double* thresholds, int nedges) {
     FB_CUDA(cudaStreamSynchronize(p->stream));
     FB_CUDA(cudaMemcpy(p->thr, thresholds, nedges * sizeof(double), cudaMemcpyHostToDevice));
     p->nedges = nedges;
+    // log-spaced edges (box.py:749)?  then a bin can be guessed from one log2 on the device
+    p->bin_l0 = 0.0;
+    p->bin_inv_d = 0.0;
+    if (nedges >= 3 && thresholds[0] > 0.0) {
+        const double l0 = log2(thresholds[0]), d = (log2(thresholds[nedges - 1]) - l0) / (nedges - 1);
+        bool ok = d > 0.0;
+        for (int i = 0; ok && i < nedges; ++i) ok = fabs(log2(thresholds[i]) - (l0 + d * i)) <= 0.25 * d;
+        if (ok) {
+            p->bin_l0 = l0;
+            p->bin_inv_d = 1.0 / d;
+        }
+    }
     return 0;
 }
 

@@ -14,6 +14,7 @@
 namespace fb {
 
 #define FB_MAX_EDGES 128
+#define FB_PK_COPIES 64      // replicas of the global P(k) histogram (power of two)
 
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
@@ -66,6 +67,7 @@ struct KSpace {
     const double* az;
     const double* thr;      // thresholds on s
     int nedges;
+    float bin_l0, bin_inv_d; // log2 model of the thresholds (0 = none, use binary search)
     double inv_boxfactor;
 };
 
@@ -91,6 +93,7 @@ struct fb_plan {
     float2* tw;
     double *ax, *ay, *az, *thr;
     int nedges;
+    double bin_l0, bin_inv_d;
     float* sqrtp;
     int sqrtp_mode;
     long sqrtp_n;

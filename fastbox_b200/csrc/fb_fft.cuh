@@ -150,11 +150,24 @@ FB_DEV void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
         if constexpr (Ns > 1) {
             const int jm = (t + u * T) & (Ns - 1);
             constexpr int step = (FB_NMAX_TW / (Ns * R));
+            if constexpr (R >= 8) {
+                // twiddles w^r, r = 1..R-1, from ONE table load: powers by a product tree of depth
+                // <= 4 (each lane's R-1 twiddles are distinct, so loading them all costs ~R sector
+                // look-ups per lane in L1 -- far more than the data itself)
+                float2 w[R];
+                w[1] = FB_LDG(&tw[jm * step]);
+                if (S > 0) w[1].y = -w[1].y;
 #pragma unroll
-            for (int r = 1; r < R; ++r) {
-                float2 w = FB_LDG(&tw[r * jm * step]);
-                if (S > 0) w.y = -w.y;
-                a[r] = cmul(a[r], w);
+                for (int r = 2; r < R; ++r) w[r] = cmul(w[r / 2], w[r - r / 2]);
+#pragma unroll
+                for (int r = 1; r < R; ++r) a[r] = cmul(a[r], w[r]);
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    float2 w = FB_LDG(&tw[r * jm * step]);
+                    if (S > 0) w.y = -w.y;
+                    a[r] = cmul(a[r], w);
+                }
             }
         }
         Dft<R, S>::run(a);

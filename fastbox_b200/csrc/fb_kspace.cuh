@@ -7,6 +7,22 @@
 
 namespace fb {
 
+// sqrt(P) from the table uniform in log2(s): Catmull-Rom cubic through 4 neighbouring nodes
+// (the table is a few tens of KB and stays in L1, unlike the exact integer LUT whose gathers go
+// to L2).  The shim validates the interpolation error against the exact values (kspace.py).
+__device__ __forceinline__ float sqrtp_logtable(const KSpace& K, float s) {
+    if (!(s > 0.f)) return 0.f;                          // nan_to_num(P(0)) = 0, box.py:167
+    float x = (__log2f(s) - K.log2s0) * K.inv_dlog2s;
+    x = fminf(fmaxf(x, 1.f), (float)(K.sqrtp_n - 3) + 0.999f);
+    const int i = (int)x;
+    const float f = x - (float)i;
+    const float p0 = __ldg(&K.sqrtp[i - 1]), p1 = __ldg(&K.sqrtp[i]), p2 = __ldg(&K.sqrtp[i + 1]),
+                p3 = __ldg(&K.sqrtp[i + 2]);
+    const float c3 = 3.f * (p1 - p2) + p3 - p0;
+    const float c2 = 2.f * p0 - 5.f * p1 + 4.f * p2 - p3;
+    return fmaf(0.5f * f, fmaf(f, fmaf(f, c3, c2), p2 - p0), p1);
+}
+
 // real multiplier for mode (a,b,c) (global indices); `cf` = index used for the k_par /
 // dense filter lookup (c itself, or (N-c)%N when the factor at -k is wanted).
 __device__ __forceinline__ float k_amp(const KSpace& K, int flags, int kind, int a, int b, int c, int cf) {
@@ -20,18 +36,7 @@ __device__ __forceinline__ float k_amp(const KSpace& K, int flags, int kind, int
     if (kind != FB_KIND_PLAIN || ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 2)) {
         s = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2 + (float)(mc * mc) * K.inv_lz2;
     }
-    if ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 2) {
-        if (s > 0.f) {
-            float x = (log2f(s) - K.log2s0) * K.inv_dlog2s;
-            x = fminf(fmaxf(x, 0.f), (float)(K.sqrtp_n - 1) - 1e-3f);
-            const int i0 = (int)x;
-            const float f = x - (float)i0;
-            const float y0 = __ldg(&K.sqrtp[i0]), y1 = __ldg(&K.sqrtp[i0 + 1]);
-            amp = fmaf(f, y1 - y0, y0);
-        } else {
-            amp = 0.f;                                   // nan_to_num(P(0)) = 0, box.py:167
-        }
-    }
+    if ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 2) amp = sqrtp_logtable(K, s);
     if (flags & FB_F_FILTER) {
         if (K.tdense)
             amp *= __ldg(&K.tdense[((size_t)a * N + b) * N + cf]);

@@ -19,7 +19,8 @@ struct RowGeom {
     static constexpr int T = C::T;
     static constexpr int RB = 256 / T;          // rows per CTA (rows are flat over (plane, b))
     static constexpr int THREADS = 256;
-    static constexpr size_t SMEM = (size_t)RB * RowLayout<N>::ROW * sizeof(float2);
+    static constexpr size_t FFT_SMEM = (size_t)RB * RowLayout<N>::ROW * sizeof(float2);
+    static constexpr size_t SMEM = FFT_SMEM + (size_t)(N + N / 16 + FB_MAX_EDGES) * sizeof(double);   // + P(k) tables
 };
 
 struct RowsArgs {
@@ -71,79 +72,104 @@ __device__ __forceinline__ void store_run(float2* __restrict__ p, const float2 (
     for (int i = 0; i < P / 2; ++i) p4[i] = make_float4(in[2 * i].x, in[2 * i].y, in[2 * i + 1].x, in[2 * i + 1].y);
 }
 
-// running P(k) moments of one thread while it walks along c
-struct PkWalk {
+// ---- P(k) moments, accumulated straight into the global (L2-resident) histogram with
+// fire-and-forget float64 / uint64 reductions (RED.ADD): no shared-memory histogram, no CTA
+// level init / flush barriers.  Thresholds are read through L1 (a few hundred bytes).
+__device__ __forceinline__ int pk_bin_g(const KSpace& K, const double* __restrict__ thr, double s) {   // #{ j : thr[j] <= s }
+    int g;
+    if (K.bin_inv_d > 0.f) {
+        // log-spaced edges (box.py:749): one log2 gives the bin, two exact comparisons confirm it
+        const float sf = (float)s;
+        g = sf > 0.f ? (int)floorf((__log2f(sf) - K.bin_l0) * K.bin_inv_d) + 1 : 0;
+        g = max(0, min(g, K.nedges));
+    } else {
+        int lo = 0, hi = K.nedges;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (thr[mid] <= s) lo = mid + 1; else hi = mid;
+        }
+        g = lo;
+    }
+    while (g < K.nedges && s >= thr[g]) ++g;
+    while (g > 0 && s < thr[g - 1]) --g;
+    return g;
+}
+
+// per-CTA shared-memory copies of the float64 tables the binning needs.  (Per-lane strided reads
+// of these through L1 cost 32 sector look-ups per warp request and dominated the kernel.)
+struct PkTables {
+    const double* az;       // (m_c/Lz)^2 at padded index c + (c >> 4)
+    const double* thr;      // bin thresholds on s
+};
+template <int N>
+struct PkSmem {
+    static constexpr int AZ = N + N / 16;
+    static constexpr size_t BYTES = (size_t)(AZ + FB_MAX_EDGES) * sizeof(double);
+};
+template <int N>
+__device__ __forceinline__ PkTables pk_stage_tables(const KSpace& K, double* sm) {
+    for (int c = threadIdx.x; c < N; c += blockDim.x) sm[c + (c >> 4)] = __ldg(&K.az[c]);
+    double* thr = sm + PkSmem<N>::AZ;
+    for (int j = threadIdx.x; j < K.nedges; j += blockDim.x) thr[j] = __ldg(&K.thr[j]);
+    PkTables t;
+    t.az = sm;
+    t.thr = thr;
+    return t;
+}
+
+struct PkAcc {
     int bin;
     unsigned cnt;
     double s1, s2, l2, l4;      // float64: a bin holding only a Hermitian pair gets stddev == 0 exactly
 };
 
-__device__ __forceinline__ void pk_walk_flush_thread(PkShared& sh, PkWalk& w, bool poles) {
-    if (w.cnt) {
-        atomicAdd(&sh.cnt[w.bin], (unsigned long long)w.cnt);
-        atomicAdd(&sh.s1[w.bin], w.s1);
-        atomicAdd(&sh.s2[w.bin], w.s2);
+__device__ __forceinline__ void pk_red(const PkDev& out, const PkAcc& a, bool poles) {
+    if (a.cnt) {
+        // replica chosen by CTA: keeps the per-address reduction rate at L2 far below its limit
+        const int i = a.bin + (int)(blockIdx.x & (FB_PK_COPIES - 1)) * (FB_MAX_EDGES + 1);
+        atomicAdd(&out.count[i], (unsigned long long)a.cnt);
+        atomicAdd(&out.sum1[i], a.s1);
+        atomicAdd(&out.sum2[i], a.s2);
         if (poles) {
-            atomicAdd(&sh.l2[w.bin], w.l2);
-            atomicAdd(&sh.l4[w.bin], w.l4);
+            atomicAdd(&out.l2[i], a.l2);
+            atomicAdd(&out.l4[i], a.l4);
         }
     }
-    w.cnt = 0u;
-    w.s1 = w.s2 = w.l2 = w.l4 = 0.0;
 }
 
-// add mode (s, p) with multiplicity wf to the walk; s is monotone along a run so the bin moves by
-// single steps (both directions are handled: |m_c| decreases for c >= N/2)
-__device__ __forceinline__ void pk_walk_add(PkShared& sh, PkWalk& w, int nedges, double s, float p, float wf,
-                                            float mu2, bool poles) {
-    int nb = w.bin;
-    while (nb < nedges && s >= sh.thr[nb]) ++nb;
-    while (nb > 0 && s < sh.thr[nb - 1]) --nb;
-    if (nb != w.bin) {
-        pk_walk_flush_thread(sh, w, poles);
-        w.bin = nb;
-    }
-    const double pd = (double)p, wp = (double)wf * pd;
-    w.cnt += (unsigned)(wf + 0.5f);
-    w.s1 += wp;
-    w.s2 += wp * pd;
-    if (poles) {
-        const double m2 = (double)mu2;
-        w.l2 += wp * (1.5 * m2 - 0.5);
-        w.l4 += wp * ((35.0 * m2 * m2 - 30.0 * m2 + 3.0) * 0.125);
-    }
-}
-
-// end of the run: lanes of a warp holding the same bin are combined before touching smem
-__device__ __forceinline__ void pk_walk_flush_warp(PkShared& sh, const PkWalk& w, bool poles, bool valid) {
+// Lanes of a warp hold consecutive runs of one row, so equal bins sit in contiguous lane
+// segments: a segmented inclusive scan (5 shuffle steps, independent of the number of bins)
+// leaves each segment's total in its last lane, which issues the reductions.
+__device__ __forceinline__ void pk_seg_flush2(const PkDev& out, PkAcc a, PkAcc b, bool valid) {
     const unsigned full = 0xffffffffu;
-    const bool have = valid && w.cnt > 0u;
-    unsigned todo = __ballot_sync(full, have);
     const int lane = threadIdx.x & 31;
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int lb = __shfl_sync(full, w.bin, leader);
-        const bool mine = have && (w.bin == lb);
-        const unsigned grp = __ballot_sync(full, mine);
-        const unsigned cnt = __reduce_add_sync(full, mine ? w.cnt : 0u);
-        const double a1 = warp_sum(mine ? w.s1 : 0.0);
-        const double a2 = warp_sum(mine ? w.s2 : 0.0);
-        double b2 = 0.0, b4 = 0.0;
-        if (poles) {
-            b2 = warp_sum(mine ? w.l2 : 0.0);
-            b4 = warp_sum(mine ? w.l4 : 0.0);
+    const int ka = (valid && a.cnt) ? a.bin : (-1 - lane);
+    const int kb = (valid && b.cnt) ? b.bin : (-1 - lane);
+    // segment = maximal run of consecutive lanes with the same bin (equal bins in non-adjacent
+    // lanes, e.g. from different rows sharing a warp, are separate segments)
+    const unsigned below = 0xffffffffu >> (31 - lane);
+    const int pa = __shfl_up_sync(full, ka, 1), pb = __shfl_up_sync(full, kb, 1);   // all lanes take part
+    const int sa = 31 - __clz(__ballot_sync(full, lane == 0 || pa != ka) & below);
+    const int sb = 31 - __clz(__ballot_sync(full, lane == 0 || pb != kb) & below);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned ca = __shfl_up_sync(full, a.cnt, d), cb = __shfl_up_sync(full, b.cnt, d);
+        const double a1 = __shfl_up_sync(full, a.s1, d), a2 = __shfl_up_sync(full, a.s2, d);
+        const double b1 = __shfl_up_sync(full, b.s1, d), b2 = __shfl_up_sync(full, b.s2, d);
+        if (lane - d >= sa) {
+            a.cnt += ca;
+            a.s1 += a1;
+            a.s2 += a2;
         }
-        if (lane == leader) {
-            atomicAdd(&sh.cnt[lb], (unsigned long long)cnt);
-            atomicAdd(&sh.s1[lb], a1);
-            atomicAdd(&sh.s2[lb], a2);
-            if (poles) {
-                atomicAdd(&sh.l2[lb], b2);
-                atomicAdd(&sh.l4[lb], b4);
-            }
+        if (lane - d >= sb) {
+            b.cnt += cb;
+            b.s1 += b1;
+            b.s2 += b2;
         }
-        todo &= ~grp;
     }
+    const int na = __shfl_down_sync(full, ka, 1), nb = __shfl_down_sync(full, kb, 1);
+    if (ka >= 0 && (lane == 31 || na != ka)) pk_red(out, a, false);
+    if (kb >= 0 && (lane == 31 || nb != kb)) pk_red(out, b, false);
 }
 
 // Per-run multiplier amp[e] for modes c0+e (sqrt(P) LUT, filter, velocity / potential factor).
@@ -167,15 +193,7 @@ __device__ __forceinline__ void run_amp(const KSpace& K, int flags, int kind, in
 #pragma unroll
             for (int e = 0; e < P; ++e) {
                 const int mc = mode_number(c0 + e, N);
-                const float s = sab + (float)(mc * mc) * K.inv_lz2;
-                float val = 0.f;                                   // nan_to_num(P(0)) = 0, box.py:167
-                if (s > 0.f) {
-                    float x = (log2f(s) - K.log2s0) * K.inv_dlog2s;
-                    x = fminf(fmaxf(x, 0.f), (float)(K.sqrtp_n - 1) - 1e-3f);
-                    const int i0 = (int)x;
-                    const float y0 = __ldg(&K.sqrtp[i0]), y1 = __ldg(&K.sqrtp[i0 + 1]);
-                    val = fmaf(x - (float)i0, y1 - y0, y0);
-                }
+                const float val = sqrtp_logtable(K, sab + (float)(mc * mc) * K.inv_lz2);
                 amp[e] *= val;
             }
         }
@@ -213,51 +231,91 @@ __device__ __forceinline__ void run_amp(const KSpace& K, int flags, int kind, in
 }
 
 // P(k) moments of one natural-order run h[0..P) (modes c0..c0+P-1 of row (a,b)), optionally
-// crossed with x[].  Fast path: first and last mode of the run fall in the same bin (s is monotone
-// along a run when T > 1), so no per-mode bin search is needed.
+// crossed with x[].  s = |k|^2/(2 pi)^2 is monotone along a run (T > 1), so a run touches the
+// bins between those of its first and last mode.  Common case (warp-uniform test): every run of
+// the warp spans at most two adjacent bins -> branch-free two-accumulator path.  Otherwise
+// (very low |k|, or multipoles requested) each lane walks its run mode by mode.
 template <int N, int P, bool MONOTONE>
-__device__ __forceinline__ void run_pk(PkShared& pks, const KSpace& K, int a, int b, int c0, const float2 (&h)[P],
-                                       const float2* x, bool poles, bool rvalid) {
+__device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, const PkDev& out, int a, int b, int c0,
+                                       const float2 (&h)[P], const float2* x, bool poles, bool rvalid) {
+    const unsigned full = 0xffffffffu;
     const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
+    const unsigned wi = (unsigned)(wmult + 0.5f);
     const double sab = __dadd_rn(K.ax[a], K.ay[b]);
     const float invb = (float)K.inv_boxfactor;
-    PkWalk walk;
-    walk.bin = 0;
-    walk.cnt = 0u;
-    walk.s1 = walk.s2 = walk.l2 = walk.l4 = 0.0;
-    const double s_first = __dadd_rn(sab, K.az[c0]), s_last = __dadd_rn(sab, K.az[c0 + P - 1]);
-    const int b0 = pk_bin(pks, K.nedges, s_first), b1 = pk_bin(pks, K.nedges, s_last);
-    if (MONOTONE && b0 == b1 && !poles) {
-        double s1 = 0.0, s2 = 0.0;
+    const double* az = tb.az + c0 + (c0 >> 4);           // (m_c/Lz)^2, shared memory, padded every 16
+    const double* thr = tb.thr;
+    const double s_first = __dadd_rn(sab, az[0]), s_last = __dadd_rn(sab, az[P - 1]);
+    const int b0 = pk_bin_g(K, thr, s_first), b1 = pk_bin_g(K, thr, s_last);
+    const int lo = min(b0, b1), hi = max(b0, b1);
+    const bool simple = MONOTONE && !poles && (hi - lo <= 1);
+    if (__all_sync(full, simple || !rvalid)) {
+        // modes with s >= cut belong to bin hi (cut = upper edge of bin lo)
+        const double cut = (hi > lo) ? thr[lo] : 1.0e300;
+        PkAcc A, B;
+        A.bin = lo; B.bin = hi;
+        A.cnt = 0u; B.cnt = 0u;
+        A.s1 = A.s2 = B.s1 = B.s2 = 0.0;
+        A.l2 = A.l4 = B.l2 = B.l4 = 0.0;
 #pragma unroll
         for (int e = 0; e < P; ++e) {
             const float p = x ? (h[e].x * x[e].x + h[e].y * x[e].y) * invb : (h[e].x * h[e].x + h[e].y * h[e].y) * invb;
             const double pd = (double)p;
-            s1 += pd;
-            s2 = fma(pd, pd, s2);
+            const bool up = __dadd_rn(sab, az[e]) >= cut;
+            const double pa = up ? 0.0 : pd, pb = up ? pd : 0.0;
+            B.cnt += up ? 1u : 0u;
+            A.s1 += pa;
+            A.s2 = fma(pa, pa, A.s2);
+            B.s1 += pb;
+            B.s2 = fma(pb, pb, B.s2);
         }
-        if (rvalid) {
-            walk.bin = b0;
-            walk.cnt = (unsigned)P * (unsigned)(wmult + 0.5f);
-            walk.s1 = (double)wmult * s1;
-            walk.s2 = (double)wmult * s2;
-        }
-    } else {
-        walk.bin = b0;
+        A.cnt = ((unsigned)P - B.cnt) * wi;
+        B.cnt *= wi;
+        A.s1 *= (double)wmult; A.s2 *= (double)wmult;
+        B.s1 *= (double)wmult; B.s2 *= (double)wmult;
+        pk_seg_flush2(out, A, B, rvalid);
+    } else if (rvalid) {
+        PkAcc w;
+        w.bin = b0;
+        w.cnt = 0u;
+        w.s1 = w.s2 = w.l2 = w.l4 = 0.0;
 #pragma unroll
         for (int e = 0; e < P; ++e) {
-            const double azc = K.az[c0 + e];
-            const double s = __dadd_rn(sab, azc);
             const float p = x ? (h[e].x * x[e].x + h[e].y * x[e].y) * invb : (h[e].x * h[e].x + h[e].y * h[e].y) * invb;
-            const float mu2 = (poles && s > 0.0) ? (float)azc / (float)s : 0.f;
-            if (rvalid) pk_walk_add(pks, walk, K.nedges, s, p, wmult, mu2, poles);
+            const double se = __dadd_rn(sab, az[e]);
+            int nb = w.bin;
+            while (nb < K.nedges && se >= thr[nb]) ++nb;
+            while (nb > 0 && se < thr[nb - 1]) --nb;
+            if (nb != w.bin) {
+                pk_red(out, w, poles);
+                w.bin = nb;
+                w.cnt = 0u;
+                w.s1 = w.s2 = w.l2 = w.l4 = 0.0;
+            }
+            const double pd = (double)p, wp = (double)wmult * pd;
+            w.cnt += wi;
+            w.s1 += wp;
+            w.s2 = fma(wp, pd, w.s2);
+            if (poles) {
+                const double m2 = se > 0.0 ? az[e] / se : 0.0;      // (k_par/k)^2
+                w.l2 += wp * (1.5 * m2 - 0.5);
+                w.l4 += wp * ((35.0 * m2 * m2 - 30.0 * m2 + 3.0) * 0.125);
+            }
         }
+        pk_red(out, w, poles);
     }
-    pk_walk_flush_warp(pks, walk, poles, rvalid);
 }
 
 // ---------------------------------------------------------------------------
 // rows, inverse.  grid = ceil(na*N / RB), block = 256
+//
+// Three thread->mode mappings are used inside one row (T threads, P modes each):
+//   quad     : c = 4t + 4T*j + e      global loads/stores: a warp touches 128 consecutive modes
+//                                     with 16-byte lanes (fully coalesced LDG/STG.128)
+//   run      : c = P*t + e            P(k) moments: one bin per run almost always
+//   stockham : c = t + T*q            the FFT itself
+// The Hermitian spectrum is built in quad order, parked in shared memory in natural order,
+// and read back in run order (moments) and Stockham order (transform).
 // ---------------------------------------------------------------------------
 template <int N, int SRC>
 __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsArgs A) {
@@ -266,7 +324,6 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsA
     constexpr int P = C::P, T = C::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
-    __shared__ PkShared pks;
 
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
     const long row_raw = (long)blockIdx.x * G::RB + rl;
@@ -277,109 +334,103 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsA
     const int b = (int)(row_id % N);
     const bool do_pk = (A.flags & FB_F_PK) != 0;
     const bool poles = (A.flags & FB_F_POLES) != 0;
-    if (do_pk) {
-        pk_shared_init(pks, A.K);
-        __syncthreads();
-    }
     const size_t row_local = ((size_t)al * N + b) * N;
     const int am = (N - a) & (N - 1), bm = (N - b) & (N - 1);
     const size_t row_g = ((size_t)a * N + b) * N, row_m = ((size_t)am * N + bm) * N;
-    const int c0 = P * t;                          // natural-order run of this thread
-    const int mstart = N - c0 - P;                 // mirror block: cells mstart .. mstart+P-1  (c -> N-c)
-    const int cm0 = (N - c0) & (N - 1);            // mirror of the first cell of the run
     const bool antiherm = (A.flags & FB_F_ANTIHERM) != 0;
-
-    // ---- 1. gather: h = G(k) +/- conj G(-k)   (the factor 1/2 is folded into amp)
-    float2 h[P];
-    if constexpr (SRC == SRC_SPEC) {
-        load_run<P>(A.src + row_local + c0, h);
-    } else {
-        float2 gm0;
-        if constexpr (SRC == SRC_NOISE) {
-            float r[P], i[P], rm[P], im[P];
-            load_run<P>(A.re + row_g + c0, r);
-            load_run<P>(A.im + row_g + c0, i);
-            load_run<P>(A.re + row_m + mstart, rm);
-            load_run<P>(A.im + row_m + mstart, im);
-            gm0 = make_float2(__ldg(&A.re[row_m + cm0]), __ldg(&A.im[row_m + cm0]));
-#pragma unroll
-            for (int e = 0; e < P; ++e) {
-                const float2 g = make_float2(r[e], i[e]);
-                const float2 gm = (e == 0) ? gm0 : make_float2(rm[P - e], im[P - e]);
-                h[e] = antiherm ? make_float2(g.y + gm.y, gm.x - g.x) : make_float2(g.x + gm.x, g.y - gm.y);
-            }
-        } else if constexpr (SRC == SRC_PHILOX) {
-            float2 mm[P];
-#pragma unroll
-            for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_g + c0 + e, h[e], h[e + 1]);
-#pragma unroll
-            for (int e = 0; e < P; e += 2) philox_normal_quad(A.seed, row_m + mstart + e, mm[e], mm[e + 1]);
-            float2 q0, q1;
-            philox_normal_quad(A.seed, (row_m + cm0) & ~(size_t)1, q0, q1);
-            gm0 = ((row_m + cm0) & 1) ? q1 : q0;
-#pragma unroll
-            for (int e = 0; e < P; ++e) {
-                const float2 g = h[e];
-                const float2 gm = (e == 0) ? gm0 : mm[P - e];
-                h[e] = antiherm ? make_float2(g.y + gm.y, gm.x - g.x) : make_float2(g.x + gm.x, g.y - gm.y);
-            }
-        } else {
-            // full complex cube; a k_par-odd filter multiplies G(k) and G(-k) differently (box.py:378)
-            float2 mm[P];
-            load_run<P>(A.src + row_g + c0, h);
-            load_run<P>(A.src + row_m + mstart, mm);
-            gm0 = __ldg(&A.src[row_m + cm0]);
-            const bool filt = (A.flags & FB_F_FILTER) != 0;
-#pragma unroll
-            for (int e = 0; e < P; ++e) {
-                float2 g = h[e];
-                float2 gm = (e == 0) ? gm0 : mm[P - e];
-                if (filt) {
-                    const int c = c0 + e, cm = (N - c) & (N - 1);
-                    const float f = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, c);
-                    const float fm = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, cm);
-                    g.x *= f; g.y *= f;
-                    gm.x *= fm; gm.y *= fm;
-                }
-                h[e] = antiherm ? make_float2(g.y + gm.y, gm.x - g.x) : make_float2(g.x + gm.x, g.y - gm.y);
-            }
-        }
-    }
-    // ---- 2. k-space multiplier
-    {
-        float amp[P];
-        const int amp_flags = (SRC == SRC_CUBE) ? (A.flags & ~FB_F_FILTER) : A.flags;
-        run_amp<N, P>(A.K, amp_flags, A.kind, a, b, c0, SRC == SRC_SPEC ? 1.f : 0.5f, amp);
-        if (A.kind >= FB_KIND_VEL_X && A.kind <= FB_KIND_VEL_Z) {          // * i, box.py:254-256
-#pragma unroll
-            for (int e = 0; e < P; ++e) h[e] = make_float2(-h[e].y * amp[e], h[e].x * amp[e]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < P; ++e) h[e] = make_float2(h[e].x * amp[e], h[e].y * amp[e]);
-        }
-    }
-    if (A.spec_out && rvalid) store_run<P>(A.spec_out + row_local + c0, h);
-    // ---- 3. binned moments of |H|^2 (box.py:741-764)
-    if (do_pk) run_pk<N, P, (T > 1)>(pks, A.K, a, b, c0, h, nullptr, poles, rvalid);
-
-    // ---- 4. natural -> Stockham order, transform c -> z, store
+    const bool velocity = (A.kind >= FB_KIND_VEL_X && A.kind <= FB_KIND_VEL_Z);
+    const int amp_flags = (SRC == SRC_CUBE) ? (A.flags & ~FB_F_FILTER) : A.flags;
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
     float2 v[P];
-    if constexpr (T > 1) {
+    PkTables tb;
+    if (do_pk) tb = pk_stage_tables<N>(A.K, reinterpret_cast<double*>(smem_raw + G::FFT_SMEM));   // visible after the barrier below
+
 #pragma unroll
-        for (int e = 0; e < P; ++e) sm[sl(c0 + e)] = h[e];
-        __syncthreads();
+    for (int j = 0; j < P / 4; ++j) {
+        const int cq = 4 * t + 4 * T * j;              // first mode of this quad
+        float2 h[4];
+        // ---- 1. gather: h = G(k) +/- conj G(-k)   (the factor 1/2 is folded into amp)
+        if constexpr (SRC == SRC_SPEC) {
+            load_run<4>(A.src + row_local + cq, h);
+        } else {
+            const int mq = N - cq - 4;                 // aligned block with the mirrors of e = 1..3
+            const int cm0 = (N - cq) & (N - 1);        // mirror of e = 0
+            float2 g[4], mm[4], gm0;
+            if constexpr (SRC == SRC_NOISE) {
+                float r[4], i[4], rm[4], im[4];
+                load_run<4>(A.re + row_g + cq, r);
+                load_run<4>(A.im + row_g + cq, i);
+                load_run<4>(A.re + row_m + mq, rm);
+                load_run<4>(A.im + row_m + mq, im);
+                gm0 = make_float2(__ldg(&A.re[row_m + cm0]), __ldg(&A.im[row_m + cm0]));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    g[e] = make_float2(r[e], i[e]);
+                    mm[e] = make_float2(rm[e], im[e]);
+                }
+            } else if constexpr (SRC == SRC_PHILOX) {
+                philox_normal_quad(A.seed, row_g + cq, g[0], g[1]);
+                philox_normal_quad(A.seed, row_g + cq + 2, g[2], g[3]);
+                philox_normal_quad(A.seed, row_m + mq, mm[0], mm[1]);
+                philox_normal_quad(A.seed, row_m + mq + 2, mm[2], mm[3]);
+                float2 unused;
+                philox_normal_quad(A.seed, row_m + cm0, gm0, unused);      // cm0 is even
+            } else {
+                load_run<4>(A.src + row_g + cq, g);
+                load_run<4>(A.src + row_m + mq, mm);
+                gm0 = __ldg(&A.src[row_m + cm0]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 x = g[e];
+                float2 y = (e == 0) ? gm0 : mm[4 - e];                     // cell N - cq - e
+                if constexpr (SRC == SRC_CUBE) {
+                    // a k_par-odd filter multiplies G(k) and G(-k) differently (box.py:378)
+                    if (A.flags & FB_F_FILTER) {
+                        const int c = cq + e, cm = (N - c) & (N - 1);
+                        const float f = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, c);
+                        const float fm = k_amp(A.K, FB_F_FILTER, FB_KIND_PLAIN, a, b, c, cm);
+                        x.x *= f; x.y *= f;
+                        y.x *= fm; y.y *= fm;
+                    }
+                }
+                h[e] = antiherm ? make_float2(x.y + y.y, y.x - x.x) : make_float2(x.x + y.x, x.y - y.y);
+            }
+        }
+        // ---- 2. k-space multiplier
+        float amp[4];
+        run_amp<N, 4>(A.K, amp_flags, A.kind, a, b, cq, SRC == SRC_SPEC ? 1.f : 0.5f, amp);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            h[e] = velocity ? make_float2(-h[e].y * amp[e], h[e].x * amp[e])      // * i, box.py:254-256
+                            : make_float2(h[e].x * amp[e], h[e].y * amp[e]);
+        if (A.spec_out && rvalid) store_run<4>(A.spec_out + row_local + cq, h);
+        if constexpr (T > 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sm[sl(cq + e)] = h[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[4 * j + e] = h[e];
+        }
+    }
+    if (T > 1 || do_pk) __syncthreads();
+    // ---- 3. binned moments of |H|^2 (box.py:741-764), run order
+    if (do_pk) {
+        const int c0 = P * t;
+        float2 hr[P];
+#pragma unroll
+        for (int e = 0; e < P; ++e) hr[e] = (T > 1) ? sm[sl(c0 + e)] : v[e];
+        run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, nullptr, poles, rvalid);
+    }
+    // ---- 4. Stockham order, transform c -> z, store
+    if constexpr (T > 1) {
         fft_exchange_read<N, P>(v, t, sm, sl);
         __syncthreads();
-    } else {
-#pragma unroll
-        for (int e = 0; e < P; ++e) v[e] = h[e];
     }
     fft_regs<N, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, A.tw);
 #pragma unroll
     for (int q = 0; q < P; ++q)
         if (rvalid) A.work[row_local + t + T * q] = v[q];
-    if (do_pk) pk_shared_flush(pks, A.K, A.pk, poles);
 }
 
 // ---------------------------------------------------------------------------
@@ -393,7 +444,6 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_fwd(const RowsA
     constexpr int P = C::P, T = C::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
-    __shared__ PkShared pks;
 
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
     const long row_raw = (long)blockIdx.x * G::RB + rl;
@@ -404,40 +454,43 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_fwd(const RowsA
     const int b = (int)(row_id % N);
     const bool do_pk = (A.flags & FB_F_PK) != 0;
     const bool poles = (A.flags & FB_F_POLES) != 0;
-    if (do_pk) {
-        pk_shared_init(pks, A.K);
-        __syncthreads();
-    }
     const size_t row_local = ((size_t)al * N + b) * N;
     float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) v[q] = A.work[row_local + t + T * q];
+    PkTables tb;
+    if (do_pk) tb = pk_stage_tables<N>(A.K, reinterpret_cast<double*>(smem_raw + G::FFT_SMEM));
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
     fft_regs<N, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, A.tw);
-    // back to natural order: thread owns c0 .. c0+P-1
-    const int c0 = P * t;
-    float2 h[P];
+    if (T == 1 && do_pk) __syncthreads();
     if constexpr (T > 1) {
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];
+        for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];         // natural order in smem
         __syncthreads();
-#pragma unroll
-        for (int e = 0; e < P; ++e) h[e] = sm[sl(c0 + e)];
-    } else {
-#pragma unroll
-        for (int e = 0; e < P; ++e) h[e] = v[e];
     }
-    if (A.spec_out && rvalid) store_run<P>(A.spec_out + row_local + c0, h);
-    if (do_pk) {
+    if (A.spec_out && rvalid) {                                      // quad order: coalesced STG.128
+#pragma unroll
+        for (int j = 0; j < P / 4; ++j) {
+            const int cq = 4 * t + 4 * T * j;
+            float2 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = (T > 1) ? sm[sl(cq + e)] : v[4 * j + e];
+            store_run<4>(A.spec_out + row_local + cq, h);
+        }
+    }
+    if (do_pk) {                                                     // run order
+        const int c0 = P * t;
+        float2 hr[P];
+#pragma unroll
+        for (int e = 0; e < P; ++e) hr[e] = (T > 1) ? sm[sl(c0 + e)] : v[e];
         if (A.cross) {
             float2 x[P];
             load_run<P>(A.cross + row_local + c0, x);
-            run_pk<N, P, (T > 1)>(pks, A.K, a, b, c0, h, x, poles, rvalid);
+            run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, x, poles, rvalid);
         } else {
-            run_pk<N, P, (T > 1)>(pks, A.K, a, b, c0, h, nullptr, poles, rvalid);
+            run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, nullptr, poles, rvalid);
         }
-        pk_shared_flush(pks, A.K, A.pk, poles);
     }
 }
 
@@ -508,11 +561,12 @@ struct XGeom {
     static constexpr int M = N / 2;
     using C = FftCfg<M>;
     static constexpr int THREADS = CZ * C::T;
+    static constexpr int MINB = THREADS >= 1024 ? 1 : (1024 / THREADS > 4 ? 4 : 1024 / THREADS);   // keep <= 64 regs
     static constexpr size_t SMEM = (size_t)(M + M / 16) * CZ * sizeof(float2);
 };
 
 template <int N, int CZ>
-__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS) k_x_c2r(const XArgs A) {
+__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x_c2r(const XArgs A) {
     constexpr int M = N / 2;
     using C = FftCfg<M>;
     constexpr int P = C::P, T = C::T;
@@ -522,18 +576,29 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS) k_x_c2r(const XArgs A) 
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
     const size_t g = (size_t)blockIdx.x * CZ + col;
     const float2* src = A.spec + g;
+    ColLayout<CZ> sl{col};
     float2 v[P];
+    // each plane element is read from HBM once; the mirrored partner X[M-k] comes from the tile
+    // parked in shared memory (plane M, the partner of k = 0, is outside the tile)
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        v[q] = src[(size_t)(t + T * q) * A.ncols];
+        sm[sl(t + T * q)] = v[q];
+    }
+    float2 xnyq = make_float2(0.f, 0.f);
+    if (t == 0) xnyq = src[(size_t)M * A.ncols];
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
-        const float2 xk = src[(size_t)k * A.ncols];
-        const float2 xm = cconj(src[(size_t)(M - k) * A.ncols]);
+        const float2 xk = v[q];
+        const float2 xm = cconj(k == 0 ? xnyq : sm[sl(M - k)]);
         float2 w = __ldg(&A.tw[k * (FB_NMAX_TW / N)]);
         w.y = -w.y;                                    // e^{+2 pi i k / N}
         const float2 sp = cadd(xk, xm), df = cmul(csub(xk, xm), w);
         v[q] = make_float2(sp.x - df.y, sp.y + df.x);  // sp + i*df
     }
-    ColLayout<CZ> sl{col};
+    if constexpr (C::R2 > 1) __syncthreads();          // the exchanges reuse the buffer
     fft_regs<M, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, A.tw);
     float* dst = A.field + g;
     const bool do_exp = (A.flags & FB_F_EXP) != 0;
@@ -579,7 +644,7 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS) k_x_c2r(const XArgs A) 
 //   X[k] = 1/2 (Z[k] + conj Z[M-k]) - i/2 e^{-2 pi i k/N} (Z[k] - conj Z[M-k]),  k = 0..M
 // ---------------------------------------------------------------------------
 template <int N, int CZ>
-__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS) k_x_r2c(const XArgs A) {
+__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x_r2c(const XArgs A) {
     constexpr int M = N / 2;
     using C = FftCfg<M>;
     constexpr int P = C::P, T = C::T;

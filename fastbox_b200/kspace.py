@@ -86,16 +86,86 @@ def sqrt_pk_int_lut(pk_of_k, N, L, boxfactor):
     return np.sqrt(pk * boxfactor).astype(np.float32)
 
 
-def sqrt_pk_log_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, npts=1 << 16):
-    """Cuboid box: table uniform in log2(s), s = sum (m/L)^2 (k = 2 pi sqrt(s))."""
-    smin = min(1.0 / Lx ** 2, 1.0 / Ly ** 2, 1.0 / Lz ** 2)
-    smax = (N / 2.0) ** 2 * (1.0 / Lx ** 2 + 1.0 / Ly ** 2 + 1.0 / Lz ** 2)
-    l0 = np.log2(smin) - 1e-3
-    l1 = np.log2(smax) + 1e-3
-    dl = (l1 - l0) / (npts - 1)
-    s = 2.0 ** (l0 + dl * np.arange(npts))
+def sqrt_pk_log_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, npts=4096):
+    """
+    Table of sqrt(P(k) boxfactor) uniform in log2(s), s = sum (m/L)^2 (k = 2 pi sqrt(s)), read
+    on the device with Catmull-Rom cubic interpolation.  Two guard nodes on each side.
+    Returns (table float32, log2s0, dlog2s).
+    """
+    s, l0, dl = log_table_nodes(N, Lx, Ly, Lz, npts)
     pk = np.nan_to_num(np.asarray(pk_of_k(TWO_PI * np.sqrt(s)), dtype=np.float64))
     return np.sqrt(pk * boxfactor).astype(np.float32), l0, dl
+
+
+def log_table_nodes(N, Lx, Ly, Lz, npts=4096):
+    """Nodes s_i = 2^(l0 + i dl) covering every |k|^2/(2 pi)^2 of the grid, 2 guard nodes per side."""
+    smin = min(1.0 / Lx ** 2, 1.0 / Ly ** 2, 1.0 / Lz ** 2)
+    smax = (N / 2.0) ** 2 * (1.0 / Lx ** 2 + 1.0 / Ly ** 2 + 1.0 / Lz ** 2)
+    dl = (np.log2(smax) - np.log2(smin)) / (npts - 5)
+    l0 = np.log2(smin) - 2.0 * dl
+    return 2.0 ** (l0 + dl * np.arange(npts)), l0, dl
+
+
+def eval_log_table(tab, l0, dl, s):
+    """Host emulation of the device interpolation (fb_kspace.cuh:sqrtp_logtable), float64."""
+    s = np.asarray(s, dtype=np.float64)
+    out = np.zeros(s.shape)
+    ok = s > 0
+    x = np.clip((np.log2(s[ok]) - l0) / dl, 1.0, tab.size - 3 + 0.999)
+    i = np.floor(x).astype(np.int64)
+    f = x - i
+    t = tab.astype(np.float64)
+    p0, p1, p2, p3 = t[i - 1], t[i], t[i + 1], t[i + 2]
+    out[ok] = p1 + 0.5 * f * (p2 - p0 + f * (2 * p0 - 5 * p1 + 4 * p2 - p3 + f * (3 * (p1 - p2) + p3 - p0)))
+    return out
+
+
+def choose_sqrt_pk_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, rtol=2e-6, exact_below=512):
+    """
+    Pick the sqrt(P) representation for the device.
+      mode 1: exact integer LUT (cubic boxes).  Its gathers miss L1, so it is used for small grids
+              and whenever the interpolated table cannot be validated;
+      mode 2: log2(s) table + cubic interpolation, validated here against the exact values at
+              every distinct |k| of a cubic box (or 2^20 random modes of a cuboid).
+    Returns (mode, table, log2s0, dlog2s).
+    """
+    cubic = (Lx == Ly == Lz)
+    if cubic and N < exact_below:
+        return 1, sqrt_pk_int_lut(pk_of_k, N, Lx, boxfactor), 0.0, 0.0
+    if cubic:
+        n2 = np.arange(1, 3 * (N // 2) ** 2 + 1, dtype=np.float64)
+        s = n2 / Lx ** 2
+    else:
+        rng = np.random.RandomState(2718)
+        m = rng.randint(-N // 2, N // 2, size=(1 << 20, 3)).astype(np.float64)
+        s = (m[:, 0] / Lx) ** 2 + (m[:, 1] / Ly) ** 2 + (m[:, 2] / Lz) ** 2
+        s = s[s > 0]
+    exact = np.sqrt(np.nan_to_num(np.asarray(pk_of_k(TWO_PI * np.sqrt(s)), dtype=np.float64)) * boxfactor)
+    scale = np.max(np.abs(exact))
+    for npts in (4096, 16384, 65536):
+        tab, l0, dl = sqrt_pk_log_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, npts)
+        err = np.max(np.abs(eval_log_table(tab, l0, dl, s) - exact) / np.maximum(np.abs(exact), 1e-6 * scale))
+        if err < rtol:
+            return 2, tab, l0, dl
+    if cubic:
+        return 1, sqrt_pk_int_lut(pk_of_k, N, Lx, boxfactor), 0.0, 0.0
+    return 2, tab, l0, dl
+
+
+def log_bin_model(thresholds):
+    """
+    If the thresholds are (numerically) uniform in log2, return (log2 t0, 1/dlog2) so that the
+    device can guess a bin with one log2 and confirm it with two exact comparisons; else (0, 0)
+    (binary search).  Exactness never depends on the guess.
+    """
+    t = np.asarray(thresholds, dtype=np.float64)
+    if t.size < 3 or np.any(t <= 0):
+        return 0.0, 0.0
+    l = np.log2(t)
+    d = (l[-1] - l[0]) / (t.size - 1)
+    if d <= 0 or np.max(np.abs(l - (l[0] + d * np.arange(t.size)))) > 0.25 * d:
+        return 0.0, 0.0
+    return float(l[0]), float(1.0 / d)
 
 
 class FilterTables(object):

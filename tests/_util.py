@@ -43,18 +43,15 @@ def transfer_fn(k_perp, k_par):                                  # reference tes
     return (1. - np.exp(-0.5 * (k_par / 0.001) ** 2.)) * np.exp(-0.5 * (k_perp / 0.1) ** 2.)
 
 
-def setup_plan(N, L, redshift, nbins=None, filt=None, device=0):
+def setup_plan(N, L, redshift, nbins=None, filt=None, device=0, exact_below=512):
     """Plan with sqrt(P) table (+ optional bins / filter) for box lengths L."""
     from fastbox_b200 import _lib
     Lx, Ly, Lz = L
     plan = _lib.Plan(N, Lx, Ly, Lz, device)
     _, pkf = pk_function(redshift)
     bf = R.boxfactor(N, Lx, Ly, Lz)
-    if Lx == Ly == Lz:
-        plan.set_sqrt_pk(ks.sqrt_pk_int_lut(pkf, N, Lx, bf), 1)
-    else:
-        tab, l0, dl = ks.sqrt_pk_log_table(pkf, N, Lx, Ly, Lz, bf)
-        plan.set_sqrt_pk(tab, 2, l0, dl)
+    mode, tab, l0, dl = ks.choose_sqrt_pk_table(pkf, N, Lx, Ly, Lz, bf, exact_below=exact_below)
+    plan.set_sqrt_pk(tab, mode, l0, dl)
     edges = None
     if nbins is not None:
         kmin, kmax = R.kmin_kmax(N, Lx, Ly, Lz)

@@ -107,6 +107,24 @@ def test_realise_filter_pk_vs_oracle(gpu, N):
     plan.close()
 
 
+def test_interpolated_sqrtp_table_and_custom_bins(gpu):
+    """Cubic box forced onto the log2(s) cubic-interpolated table (the N >= 512 default) + non-log bins."""
+    N, L = 128, (1e3, 1e3, 1e3)
+    re, im = draw_noise(3, N)
+    _, pkf = pk_function(0.8)
+    plan, _ = setup_plan(N, L, 0.8, exact_below=0)
+    kbins = np.concatenate([[0.0], np.linspace(0.01, 0.9, 24)])        # arbitrary edges (box.py:745-746)
+    plan.set_pk_bins(ks.bin_thresholds(kbins))
+    field = np.empty((N, N, N), np.float32)
+    res, _ = plan.realise(re.astype(np.float32), im.astype(np.float32), field_out=field, want_pk=True)
+    ref, half = R.realise_density_lean(re, im, pkf, N, *L)
+    assert rel_l2(field, ref) < TOL
+    kc, pk, err, cnt = R.binned_power_spectrum_lean(half, N, *L, kbins=kbins)
+    assert np.array_equal(res["count"][:kbins.size].astype(np.int64), cnt[:kbins.size])
+    assert_pk_close(ks.moments_to_spectrum(kbins, res["count"], res["sum1"], res["sum2"]), (kc, pk, err))
+    plan.close()
+
+
 @pytest.mark.parametrize("N", [32, 64])
 def test_forward_pk_and_cross(gpu, N):
     L = (5e2, 5e2, 5e2)

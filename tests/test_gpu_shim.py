@@ -1,0 +1,146 @@
+"""
+The reference's own test-suite (fastbox/tests/test_box.py) ported onto the drop-in, plus parity of
+the drop-in's results against the golden vectors produced by the unmodified reference.
+"""
+import numpy as np
+import pytest
+
+import fastbox_b200 as fb
+from fastbox_b200.box import CosmoBox, default_cosmo
+
+from _util import TOL, load_golden, rel_l2, transfer_fn
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gaussian_box(gpu):                               # test_box.py:7-38
+    np.random.seed(11)
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(1e2, 1e2, 1e2), nsamp=16, realise_now=False)
+    box.realise_density()
+    assert box.delta_x.shape == (16, 16, 16)
+    assert box.delta_x.dtype == np.float64
+    assert np.all(~np.isnan(box.delta_x))
+    np.random.seed(11)
+    box2 = CosmoBox(cosmo=default_cosmo, box_scale=1e2, nsamp=16, redshift=0., realise_now=True)
+    assert np.allclose(box.delta_x, box2.delta_x)
+    assert box.Lx == box.Ly == box.Lz == 1e2
+    assert box.x.size == box.y.size == box.z.size == 16
+    box3 = CosmoBox(cosmo=default_cosmo, box_scale=(1e2, 2e2, 1e3), nsamp=16, redshift=1., realise_now=True)
+    assert box3.delta_x.shape == (16, 16, 16) and box3.delta_x.dtype == np.float64
+    assert np.all(~np.isnan(box3.delta_x))
+    # parity with the reference run on the same seed
+    g = load_golden("n16_cubic")
+    assert rel_l2(box.delta_x, g["delta_x"]) < TOL
+    assert rel_l2(np.asarray(box.delta_k)[:9], g["delta_k_half"]) < TOL
+    full = np.fft.fftn(g["delta_x"])
+    assert rel_l2(np.asarray(box.delta_k), full) < TOL
+
+
+def test_lognormal_box(gpu):                              # test_box.py:41-55
+    np.random.seed(11)
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(1e2, 1e2, 1e2), nsamp=16, realise_now=True)
+    delta_log = box.lognormal(box.delta_x)
+    assert delta_log.shape == (16, 16, 16)
+    assert np.all(~np.isnan(delta_log)) and np.all(delta_log >= -1.)
+    g = load_golden("n16_cubic")
+    tr = fb.tracers.HITracer(box)
+    assert rel_l2(box.lognormal(box.delta_x * tr.bias_HI()), g["lognormal"]) < TOL
+
+
+def test_box_redshift_space_density(gpu):                 # test_box.py:58-76
+    np.random.seed(11)
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(1e2, 1e2, 1e2), nsamp=16, realise_now=False)
+    box.realise_density()
+    box.realise_velocity()
+    vel_z = np.fft.ifftn(box.velocity_k[2]).real           # the reference idiom still works
+    assert rel_l2(vel_z, box.velocity_k[2].real_space()) < TOL
+    g = load_golden("n16_cubic")
+    assert rel_l2(vel_z, g["vel_z"]) < TOL
+    delta_s = box.redshift_space_density(delta_x=box.delta_x, velocity_z=vel_z, sigma_nl=200., method='linear')
+    assert delta_s.shape == (16, 16, 16) and np.all(~np.isnan(delta_s))
+    # sigma_nl = 0 against the reference
+    tr = fb.tracers.HITracer(box)
+    ln = box.lognormal(box.delta_x * tr.bias_HI())
+    ds0 = box.redshift_space_density(delta_x=ln, velocity_z=vel_z, sigma_nl=0.)
+    assert rel_l2(ds0, g["rsd0"]) < 100 * TOL              # float32 inputs move a few interpolation nodes
+    np.random.seed(111)
+    ds120 = box.redshift_space_density(delta_x=ln, velocity_z=vel_z, sigma_nl=120.)
+    assert rel_l2(ds120, g["rsd120"]) < 100 * TOL
+
+
+def test_box_transfer_function(gpu):                      # test_box.py:79-96
+    np.random.seed(11)
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(1e2, 1e2, 1e2), nsamp=16, realise_now=True)
+    delta_smoothed = box.apply_transfer_fn(box.delta_k, transfer_fn=transfer_fn)
+    assert delta_smoothed.shape == (16, 16, 16) and np.iscomplexobj(delta_smoothed)
+    assert np.all(~np.isnan(delta_smoothed))
+    g = load_golden("n16_cubic")
+    assert rel_l2(delta_smoothed.real, g["transfer"]) < TOL
+    # the same through a plain complex array (general path, box.py:378-380)
+    ds2 = box.apply_transfer_fn(np.asarray(box.delta_k), transfer_fn=transfer_fn)
+    assert rel_l2(ds2.real, g["transfer"]) < TOL and np.abs(ds2.imag).max() < 1e-5 * np.abs(ds2.real).max()
+    assert rel_l2(box.smooth_field(box.delta_k, 8.0).real, g["smooth8"]) < TOL
+
+
+def test_box_power_spectrum(gpu):                         # test_box.py:99-122
+    np.random.seed(14)
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(1e3, 1e3, 1e3), nsamp=64, realise_now=False)
+    box.realise_density()
+    re_k, re_pk, re_stddev = box.binned_power_spectrum()
+    th_k, th_pk = box.theoretical_power_spectrum()
+    assert re_k.size == re_pk.size == re_stddev.size == 19
+    sigR = box.sigmaR(R=8.)
+    sig8 = box.sigma8()
+    assert np.isclose(sigR, sig8)
+    box.test_sampling_error()
+    assert np.abs(sig8 - box.cosmo['sigma8']) < 0.09
+    # the three input conventions agree (box.py:735-738)
+    k2, pk2, _ = box.binned_power_spectrum(delta_x=box.delta_x)
+    k3, pk3, _ = box.binned_power_spectrum(delta_k=np.asarray(box.delta_k))
+    m = ~np.isnan(re_pk)
+    assert np.allclose(pk2[m], re_pk[m], rtol=1e-5) and np.allclose(pk3[m], re_pk[m], rtol=1e-5)
+    with pytest.raises(ValueError):
+        box.binned_power_spectrum(delta_x=box.delta_x, delta_k=box.delta_k)
+
+
+def test_power_spectrum_golden(gpu):
+    g = load_golden("n32_gpc")
+    np.random.seed(int(g["seed"]))
+    box = CosmoBox(cosmo=default_cosmo, box_scale=1e3, nsamp=32, redshift=0.8, realise_now=False)
+    box.realise_density()
+    for nb in (20, 50):
+        kc, pk, err = box.binned_power_spectrum(nbins=nb)
+        ref = g["pk%d_p" % nb]
+        m = ~np.isnan(ref)
+        assert np.array_equal(np.isnan(pk), np.isnan(ref))
+        assert np.allclose(kc, g["pk%d_k" % nb], rtol=1e-14)
+        assert np.all(np.abs(pk[m] - ref[m]) <= 2 * TOL * np.abs(ref[m]))
+
+
+def test_box_builtin_tests(gpu):                          # test_box.py:166-174
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(1e2, 1e2, 1e2), nsamp=16, realise_now=True)
+    s1, s2 = box.test_parseval()
+    assert np.isclose(s1, s2, rtol=1e-5)
+
+
+def test_halos_and_philox_seed(gpu):
+    np.random.seed(10)
+    box = CosmoBox(cosmo=default_cosmo, box_scale=(2e3, 2e3, 2e3), nsamp=64, realise_now=False)
+    box.realise_density()
+    halos = fb.halos.HaloDistribution(box, mass_range=(1e12, 1e15), mass_bins=10)
+    np.random.seed(3)
+    Nh = halos.halo_count_field(box.delta_x, nbar=1e-3, bias=1.)          # example_halos.py:28
+    assert Nh.shape == (64, 64, 64) and Nh.dtype == np.int64 and Nh.min() >= 0
+    vol = box.Lx * box.Ly * box.Lz / 64 ** 3
+    lam = np.clip(vol * 1e-3 * (1. + box.delta_x), 0, None)
+    assert abs(Nh.mean() / lam.mean() - 1) < 0.01                        # Poisson mean
+    assert abs((Nh - lam).var() / lam.mean() - 1) < 0.05                 # Poisson variance
+    cat = halos.realise_halo_catalogue(Nh, scatter=True)
+    assert cat.shape == (Nh.sum(), 3) and cat.min() >= 0 and cat.max() < 2e3
+    # device Philox noise: reproducible, correct spectrum
+    d1 = box.realise_density(seed=99)
+    d2 = box.realise_density(seed=99)
+    assert np.array_equal(d1, d2)
+    k, pk, _ = box.binned_power_spectrum()
+    _, th = box.theoretical_power_spectrum()
+    assert np.all(np.isfinite(pk[~np.isnan(pk)]))

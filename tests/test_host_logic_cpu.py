@@ -57,12 +57,28 @@ def test_sqrt_pk_tables():
     ref = R.sqrt_pk_half(pkf, 16, 1e2, 2e2, 1e3)
     mm = ks.mode_numbers(16).astype(np.float64)
     s = (mm[:9, None, None] / 1e2) ** 2 + (mm[None, :, None] / 2e2) ** 2 + (mm[None, None, :] / 1e3) ** 2
-    with np.errstate(divide="ignore"):
-        x = (np.log2(s) - l0) / dl
-    i0 = np.clip(np.floor(x), 0, tab.size - 2).astype(int)
-    interp = tab[i0] + (x - i0) * (tab[i0 + 1] - tab[i0])
+    interp = ks.eval_log_table(tab, l0, dl, s)
     ok = s > 0
-    assert np.allclose(interp[ok], ref[ok], rtol=1e-5)
+    assert np.allclose(interp[ok], ref[ok], rtol=2e-6)
+    assert np.all(interp[~ok] == 0.0)
+    # the chooser validates the interpolated table and keeps small cubic grids exact
+    assert ks.choose_sqrt_pk_table(pkf, 32, 500., 500., 500., bf)[0] == 1
+    mode, t2, a0, d0 = ks.choose_sqrt_pk_table(pkf, 32, 500., 500., 500., bf, exact_below=0)
+    assert mode == 2 and t2.size == 4096
+    spiky = lambda k: pkf(k) * (1.0 + 0.9 * np.sin(k * 2.0e4))          # cannot be interpolated: falls back
+    assert ks.choose_sqrt_pk_table(spiky, 32, 500., 500., 500., bf, exact_below=0)[0] == 1
+
+
+def test_log_bin_model():
+    thr = ks.bin_thresholds(ks.pk_bin_edges(2 * np.pi / 2e3, 2 * np.pi * np.sqrt(3.) * 1024 / 2e3, 50))
+    l0, inv = ks.log_bin_model(thr)
+    assert inv > 0
+    s = np.exp(np.random.RandomState(0).uniform(np.log(thr[0]) - 1, np.log(thr[-1]) + 1, 100000))
+    guess = np.clip(np.floor((np.log2(s.astype(np.float32)) - np.float32(l0)) * np.float32(inv)).astype(int) + 1, 0, 50)
+    exact = np.searchsorted(thr, s, side="right")
+    assert np.max(np.abs(guess - exact)) <= 1               # the device corrects by at most one step
+    assert ks.log_bin_model(np.array([0.0, 1.0, 2.0])) == (0.0, 0.0)
+    assert ks.log_bin_model(np.array([1.0, 2.0, 3.0, 10.0])) == (0.0, 0.0)
 
 
 def test_filter_tables_separable_and_dense():

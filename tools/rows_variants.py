@@ -11,10 +11,11 @@ from fastbox_b200 import kspace as ks  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 L = 2000.0
 plan = _lib.Plan(N, L, L, L)
-n2 = np.arange(3 * (N // 2) ** 2 + 1, dtype=np.float64)
-k = 2 * np.pi * np.sqrt(n2) / L
-lut = np.where(k > 0, 1e4 * (k / 0.02) / (1 + (k / 0.02) ** 2.5), 0.0)
-plan.set_sqrt_pk(np.sqrt(lut * N ** 6. / L ** 3).astype(np.float32), 1)
+pkf = lambda k: np.where(k > 0, 1e4 * (k / 0.02) / (1 + (k / 0.02) ** 2.5), 0.0)
+with np.errstate(all="ignore"):
+    mode, tab, l0, dl = ks.choose_sqrt_pk_table(pkf, N, L, L, L, N ** 6. / L ** 3,
+                                                exact_below=int(os.environ.get("FB_EXACT_BELOW", "512")))
+plan.set_sqrt_pk(tab, mode, l0, dl)
 plan.set_pk_bins(ks.bin_thresholds(ks.pk_bin_edges(2 * np.pi / L, 2 * np.pi * np.sqrt(3.) * N / L, 50)))
 m = ks.mode_numbers(N).astype(np.float64)
 h = N // 2 + 1
