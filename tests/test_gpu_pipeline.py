@@ -248,3 +248,37 @@ def test_halo_counts_bit_exact(gpu, lognormal):
     if lognormal:
         assert rel_l2(mean_out, g[key]) < TOL
     plan.close()
+
+
+@pytest.mark.parametrize("name", ["n16_cubic", "n32_gpc"])
+def test_beam_convolve_golden(gpu, name):
+    """BeamModel.convolve_fft (beams.py:81-87) against the unmodified reference's output."""
+    from oracle.make_golden import beam_cube
+    g = load_golden(name)
+    N, L = int(g["N"]), _case_L(g)
+    plan = _lib.Plan(N, *L)
+    out = np.empty((N, N, N), np.float32)
+    plan.beam_convolve(beam_cube(N).astype(np.float32), g["rsd0"].astype(np.float32), out)
+    assert rel_l2(out, g["beam_conv"]) < TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("N", [8, 64, 128])
+def test_beam_convolve_vs_oracle(gpu, N):
+    rng = np.random.default_rng(N)
+    field = rng.standard_normal((N, N, N)).astype(np.float32)
+    x = np.arange(N) - N / 2. + 0.5
+    s = 1.0 + 3.0 * np.arange(N) / N
+    beam = (np.exp(-0.5 * (x[:, None, None] ** 2 + (x[None, :, None] - 0.7) ** 2) / s[None, None, :] ** 2)
+            * (1 + 0.1 * np.cos(x[:, None, None]))).astype(np.float32)      # not symmetric: checks the crop offset
+    plan = _lib.Plan(N, 1e3, 1e3, 1e3)
+    out = np.empty((N, N, N), np.float32)
+    plan.beam_convolve(beam, field, out)
+    ref = R.convolve_fft(beam.astype(np.float64), field.astype(np.float64))
+    assert rel_l2(out, ref) < TOL
+    # and through scipy itself, the call the reference makes
+    import scipy.signal
+    ref2 = scipy.signal.fftconvolve(beam.astype(np.float64), field.astype(np.float64), mode='same', axes=[0, 1]) \
+        / np.sum(beam.astype(np.float64).reshape(-1, N), axis=0)[None, None, :]
+    assert rel_l2(out, ref2) < TOL
+    plan.close()

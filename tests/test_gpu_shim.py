@@ -144,3 +144,22 @@ def test_halos_and_philox_seed(gpu):
     k, pk, _ = box.binned_power_spectrum()
     _, th = box.theoretical_power_spectrum()
     assert np.all(np.isfinite(pk[~np.isnan(pk)]))
+
+
+def test_beam_model_convolve_fft(gpu):
+    """fastbox/beams.py:63-87 through the drop-in class (unit beam default + a Gaussian beam)."""
+    g = load_golden("n32_gpc")
+    np.random.seed(int(g["seed"]))
+    box = CosmoBox(cosmo=default_cosmo, box_scale=1e3, nsamp=32, redshift=0.8, realise_now=False)
+    from oracle.make_golden import beam_cube
+
+    class GaussBeam(fb.beams.BeamModel):
+        def beam_cube(self, pol=None):
+            return beam_cube(32)
+    sm = GaussBeam(box).convolve_fft(g["rsd0"])
+    assert sm.dtype == np.float64 and rel_l2(sm, g["beam_conv"]) < TOL
+    gb = fb.beams.GaussianBeamModel(box)
+    cube = gb.beam_cube()
+    assert cube.shape == (32, 32, 32) and np.all(cube > 0) and np.all(cube <= 1)
+    flat = fb.beams.BeamModel(box).convolve_fft(np.ones((32, 32, 32)))
+    assert np.all(flat > 0) and flat.max() <= 1.0 + 1e-6          # unit beam: fraction of the padded frame covered

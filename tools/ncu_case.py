@@ -9,7 +9,7 @@ from fastbox_b200 import _lib  # noqa: E402
 from fastbox_b200 import kspace as ks  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-mode = sys.argv[2] if len(sys.argv) > 2 else "philox"
+src_mode = sys.argv[2] if len(sys.argv) > 2 else "philox"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 L = 2000.0
 plan = _lib.Plan(N, L, L, L)
@@ -26,7 +26,7 @@ kpar = 2 * np.pi * m / L
 plan.set_filter(np.exp(-0.5 * (kperp / 0.1) ** 2), 1. - np.exp(-0.5 * (kpar / 0.001) ** 2), None)
 field = plan.alloc(N ** 3 * 4)
 re = im = None
-if mode == "noise":
+if src_mode == "noise":
     re = plan.alloc(N ** 3 * 4)
     im = plan.alloc(N ** 3 * 4)
 for it in range(reps):
