@@ -13,15 +13,19 @@ template <int N, int CZ>
 static int launch_cols_t(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign) {
     using G = ColGeom<N, CZ>;
     dim3 grid(N / CZ, nplanes);
-    if (sign < 0) {
-        auto kern = k_cols_c2c<N, CZ, -1>;
-        if (set_smem(kern, G::SMEM)) return -2;
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(in, out, in_ny, out_ny, p->tw);
-    } else {
-        auto kern = k_cols_c2c<N, CZ, +1>;
-        if (set_smem(kern, G::SMEM)) return -2;
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(in, out, in_ny, out_ny, p->tw);
+    const bool slab = in_ny != 0 || out_ny != 0;
+#define FB_COLS_LAUNCH(SIGN_, SLAB_)                                                         \
+    {                                                                                        \
+        auto kern = k_cols_c2c<N, CZ, SIGN_, SLAB_>;                                         \
+        if (set_smem(kern, G::SMEM)) return -2;                                              \
+        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(in, out, in_ny, out_ny, p->tw);       \
     }
+    if (sign < 0) {
+        if (slab) FB_COLS_LAUNCH(-1, true) else FB_COLS_LAUNCH(-1, false)
+    } else {
+        if (slab) FB_COLS_LAUNCH(+1, true) else FB_COLS_LAUNCH(+1, false)
+    }
+#undef FB_COLS_LAUNCH
     FB_LAUNCH_CHECK();
     return 0;
 }

@@ -153,17 +153,21 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     c[3] = lo0;
 }
 __device__ __forceinline__ float2 box_muller(uint32_t x0, uint32_t x1) {
-    // u in (0,1): fl((x0 + 0.5) 2^-32) built from two exact pieces
+    // u in (0,1): fl((x0 + 0.5) 2^-32) built from two exact pieces; fast intrinsics (MUFU): the
+    // absolute error of a normal is ~5e-7, far inside the 1e-5 field tolerance
     const float u = (float)(x0 >> 8) * 5.9604644775390625e-08f + ((float)(x0 & 0xffu) + 0.5f) * 2.3283064365386963e-10f;
-    const float r = sqrtf(-2.0f * logf(u));
+    const float r = sqrtf(-2.0f * __logf(u));
     float s, co;
-    sincospif(2.0f * (((float)x1 + 0.5f) * 2.3283064365386963e-10f), &s, &co);
-    return make_float2(r * co, r * s);
+    __sincosf(6.283185307179586f * (((float)x1 + 0.5f) * 2.3283064365386963e-10f) - 3.141592653589793f, &s, &co);
+    return make_float2(-r * co, -r * s);             // cos(t) = -cos(t - pi), sin(t) = -sin(t - pi)
 }
-// White noise W = (re, im) of the two cells (index, index+1), index even: one Philox4x32-10
-// block (counter = index/2, key = seed) feeds both cells (words 0,1 -> cell index; 2,3 -> index+1).
-__device__ __forceinline__ void philox_normal_quad(uint64_t seed, uint64_t index, float2& w0, float2& w1) {
-    const uint64_t ctr = index >> 1;
+// White noise of the conjugate pair of modes k and -k from ONE Philox4x32-10 block: counter =
+// min(index(k), index(-k)), key = seed; the mode whose linear index is the smaller one takes
+// words (0,1), the other words (2,3).  H(k) = 1/2 [W(k) + conj W(-k)] thus costs one block per
+// mode, on any GPU count (the stream depends only on the global cell index).
+__device__ __forceinline__ void philox_mode_pair(uint64_t seed, uint64_t idx_k, uint64_t idx_mk, float2& wk,
+                                                 float2& wmk) {
+    const uint64_t ctr = idx_k < idx_mk ? idx_k : idx_mk;
     uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -172,8 +176,17 @@ __device__ __forceinline__ void philox_normal_quad(uint64_t seed, uint64_t index
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    w0 = box_muller(c[0], c[1]);
-    w1 = box_muller(c[2], c[3]);
+    const float2 first = box_muller(c[0], c[1]), second = box_muller(c[2], c[3]);
+    if (idx_k == idx_mk) {
+        wk = first;
+        wmk = first;
+    } else if (idx_k < idx_mk) {
+        wk = first;
+        wmk = second;
+    } else {
+        wk = second;
+        wmk = first;
+    }
 }
 
 }  // namespace fb

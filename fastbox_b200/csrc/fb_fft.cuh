@@ -126,16 +126,21 @@ struct Dft {
 //   ColLayout : CZ FFTs interleaved (element-major), one pad row every 16 elements so
 //               that the stride-16 Stockham writes of narrow tiles (CZ = 4, 8) spread over banks.
 // ---------------------------------------------------------------------------
+// Both layouts are linear in the logical index except for the pad every 16 elements, so
+//   phys(i0 + r*S) = phys(i0) + r*pstride(S)   when S % 16 == 0, or S == 1 with i0 % 16 == 0, r < 16.
+// The exchange code uses this to address a whole butterfly from one base (no shifts per access).
 template <int n>
 struct RowLayout {
     static constexpr int ROW = n + n / 16;
     int base;
     FB_DEV int operator()(int i) const { return base + i + (i >> 4); }
+    __host__ __device__ static constexpr int pstride(int S) { return S % 16 == 0 ? S + S / 16 : S; }
 };
 template <int CZ>
 struct ColLayout {
     int col;
     FB_DEV int operator()(int i) const { return (i + (i >> 4)) * CZ + col; }   // one padded row per 16
+    __host__ __device__ static constexpr int pstride(int S) { return (S % 16 == 0 ? S + S / 16 : S) * CZ; }
 };
 
 template <int n, int P, int R, int Ns, int S>
@@ -181,20 +186,44 @@ template <int n, int P, int R, int Ns, class SL>
 FB_DEV void fft_exchange_write(const float2 (&v)[P], int t, float2* sm, const SL& sl) {
     constexpr int T = n / P;
     constexpr int B = P / R;
+    static_assert(Ns % 16 == 0 || (Ns == 1 && R == 16), "exchange strides assume radix-16 first stages");
+    constexpr int PS = SL::pstride(Ns);
 #pragma unroll
     for (int u = 0; u < B; ++u) {
         const int j = t + u * T;
         const int j0 = (j / Ns) * (Ns * R) + (j & (Ns - 1));
+        float2* p = sm + sl(j0);
 #pragma unroll
-        for (int r = 0; r < R; ++r) sm[sl(j0 + r * Ns)] = v[u + r * B];
+        for (int r = 0; r < R; ++r) p[r * PS] = v[u + r * B];
     }
 }
 // ... and read back the inputs of the next stage (thread t owns elements t + T*q).
 template <int n, int P, class SL>
 FB_DEV void fft_exchange_read(float2 (&v)[P], int t, const float2* sm, const SL& sl) {
     constexpr int T = n / P;
+    if constexpr (T % 16 == 0) {
+        const float2* p = sm + sl(t);
+        constexpr int PS = SL::pstride(T);
 #pragma unroll
-    for (int q = 0; q < P; ++q) v[q] = sm[sl(t + T * q)];
+        for (int q = 0; q < P; ++q) v[q] = p[q * PS];
+    } else {
+#pragma unroll
+        for (int q = 0; q < P; ++q) v[q] = sm[sl(t + T * q)];
+    }
+}
+// store thread-owned elements t + T*q at their natural positions
+template <int n, int P, class SL>
+FB_DEV void fft_store_natural(const float2 (&v)[P], int t, float2* sm, const SL& sl) {
+    constexpr int T = n / P;
+    if constexpr (T % 16 == 0) {
+        float2* p = sm + sl(t);
+        constexpr int PS = SL::pstride(T);
+#pragma unroll
+        for (int q = 0; q < P; ++q) p[q * PS] = v[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];
+    }
 }
 // Two barriers: the buffer is reused in place.
 template <int n, int P, int R, int Ns, class SL>

@@ -13,6 +13,10 @@ namespace fb {
 
 enum { SRC_NOISE = 0, SRC_PHILOX = 1, SRC_SPEC = 2, SRC_CUBE = 3 };
 
+#ifndef FB_ROWS_MINB
+#define FB_ROWS_MINB 3      // CTAs per SM the row kernels are compiled for (register cap 65536/(256*MINB))
+#endif
+
 template <int N>
 struct RowGeom {
     using C = FftCfg<N>;
@@ -250,27 +254,41 @@ __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, cons
     const int lo = min(b0, b1), hi = max(b0, b1);
     const bool simple = MONOTONE && !poles && (hi - lo <= 1);
     if (__all_sync(full, simple || !rvalid)) {
-        // modes with s >= cut belong to bin hi (cut = upper edge of bin lo)
-        const double cut = (hi > lo) ? thr[lo] : 1.0e300;
+        // s is monotone along the run, so the run splits at one index: the first kx modes (in the
+        // direction of increasing s) fall in bin lo, the rest in bin hi.  kx comes from a 4-step
+        // binary search on the shared-memory table; accumulation is then predicated on constants.
+        const bool rising = s_last >= s_first;
+        int kx = P;                                      // number of modes with s < cut
+        if (hi > lo) {
+            const double cut = thr[lo];                  // upper edge of bin lo
+            int lo_i = 0, hi_i = P;                      // first position (in rising order) with s >= cut
+            while (lo_i < hi_i) {
+                const int mid = (lo_i + hi_i) >> 1;
+                const double sm_ = __dadd_rn(sab, az[rising ? mid : P - 1 - mid]);
+                if (sm_ < cut) lo_i = mid + 1; else hi_i = mid;
+            }
+            kx = lo_i;
+        }
+        // position of element e in rising order: e (rising) or P-1-e (falling); "low" iff position < kx
+        const int e_lo = rising ? 0 : P - kx, e_hi = rising ? kx : P;       // elements [e_lo, e_hi) are in bin lo
         PkAcc A, B;
         A.bin = lo; B.bin = hi;
-        A.cnt = 0u; B.cnt = 0u;
         A.s1 = A.s2 = B.s1 = B.s2 = 0.0;
         A.l2 = A.l4 = B.l2 = B.l4 = 0.0;
 #pragma unroll
         for (int e = 0; e < P; ++e) {
             const float p = x ? (h[e].x * x[e].x + h[e].y * x[e].y) * invb : (h[e].x * h[e].x + h[e].y * h[e].y) * invb;
             const double pd = (double)p;
-            const bool up = __dadd_rn(sab, az[e]) >= cut;
-            const double pa = up ? 0.0 : pd, pb = up ? pd : 0.0;
-            B.cnt += up ? 1u : 0u;
-            A.s1 += pa;
-            A.s2 = fma(pa, pa, A.s2);
-            B.s1 += pb;
-            B.s2 = fma(pb, pb, B.s2);
+            if (e >= e_lo && e < e_hi) {
+                A.s1 += pd;
+                A.s2 = fma(pd, pd, A.s2);
+            } else {
+                B.s1 += pd;
+                B.s2 = fma(pd, pd, B.s2);
+            }
         }
-        A.cnt = ((unsigned)P - B.cnt) * wi;
-        B.cnt *= wi;
+        A.cnt = (unsigned)kx * wi;
+        B.cnt = (unsigned)(P - kx) * wi;
         A.s1 *= (double)wmult; A.s2 *= (double)wmult;
         B.s1 *= (double)wmult; B.s2 *= (double)wmult;
         pk_seg_flush2(out, A, B, rvalid);
@@ -318,7 +336,7 @@ __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, cons
 // and read back in run order (moments) and Stockham order (transform).
 // ---------------------------------------------------------------------------
 template <int N, int SRC>
-__global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsArgs A) {
+__global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(const RowsArgs A) {
     using G = RowGeom<N>;
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
@@ -369,12 +387,10 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsA
                     mm[e] = make_float2(rm[e], im[e]);
                 }
             } else if constexpr (SRC == SRC_PHILOX) {
-                philox_normal_quad(A.seed, row_g + cq, g[0], g[1]);
-                philox_normal_quad(A.seed, row_g + cq + 2, g[2], g[3]);
-                philox_normal_quad(A.seed, row_m + mq, mm[0], mm[1]);
-                philox_normal_quad(A.seed, row_m + mq + 2, mm[2], mm[3]);
-                float2 unused;
-                philox_normal_quad(A.seed, row_m + cm0, gm0, unused);      // cm0 is even
+                philox_mode_pair(A.seed, row_g + cq, row_m + cm0, g[0], gm0);
+#pragma unroll
+                for (int e = 1; e < 4; ++e) philox_mode_pair(A.seed, row_g + cq + e, row_m + mq + 4 - e, g[e], mm[4 - e]);
+                mm[0] = gm0;
             } else {
                 load_run<4>(A.src + row_g + cq, g);
                 load_run<4>(A.src + row_m + mq, mm);
@@ -406,8 +422,9 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsA
                             : make_float2(h[e].x * amp[e], h[e].y * amp[e]);
         if (A.spec_out && rvalid) store_run<4>(A.spec_out + row_local + cq, h);
         if constexpr (T > 1) {
+            float2* pq = sm + sl(cq);                    // a quad never straddles a pad
 #pragma unroll
-            for (int e = 0; e < 4; ++e) sm[sl(cq + e)] = h[e];
+            for (int e = 0; e < 4; ++e) pq[e] = h[e];
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[4 * j + e] = h[e];
@@ -418,8 +435,9 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsA
     if (do_pk) {
         const int c0 = P * t;
         float2 hr[P];
+        const float2* pr = sm + sl(c0);                  // P consecutive modes, c0 % 16 == 0 (P == 16 when T > 1)
 #pragma unroll
-        for (int e = 0; e < P; ++e) hr[e] = (T > 1) ? sm[sl(c0 + e)] : v[e];
+        for (int e = 0; e < P; ++e) hr[e] = (T > 1) ? pr[e] : v[e];
         run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, nullptr, poles, rvalid);
     }
     // ---- 4. Stockham order, transform c -> z, store
@@ -438,7 +456,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_inv(const RowsA
 // (auto |S|^2 or cross Re S conj(X)).   grid = ceil(na*N / RB)
 // ---------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_fwd(const RowsArgs A) {
+__global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_fwd(const RowsArgs A) {
     using G = RowGeom<N>;
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
@@ -465,8 +483,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_fwd(const RowsA
     if (T == 1 && do_pk) __syncthreads();
     if constexpr (T > 1) {
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];         // natural order in smem
+        fft_store_natural<N, P>(v, t, sm, sl);                       // natural order in smem
         __syncthreads();
     }
     if (A.spec_out && rvalid) {                                      // quad order: coalesced STG.128
@@ -474,16 +491,18 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, 3) k_rows_fwd(const RowsA
         for (int j = 0; j < P / 4; ++j) {
             const int cq = 4 * t + 4 * T * j;
             float2 h[4];
+            const float2* pq = sm + sl(cq);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = (T > 1) ? sm[sl(cq + e)] : v[4 * j + e];
+            for (int e = 0; e < 4; ++e) h[e] = (T > 1) ? pq[e] : v[4 * j + e];
             store_run<4>(A.spec_out + row_local + cq, h);
         }
     }
     if (do_pk) {                                                     // run order
         const int c0 = P * t;
         float2 hr[P];
+        const float2* pr = sm + sl(c0);
 #pragma unroll
-        for (int e = 0; e < P; ++e) hr[e] = (T > 1) ? sm[sl(c0 + e)] : v[e];
+        for (int e = 0; e < P; ++e) hr[e] = (T > 1) ? pr[e] : v[e];
         if (A.cross) {
             float2 x[P];
             load_run<P>(A.cross + row_local + c0, x);
@@ -515,7 +534,7 @@ __device__ __forceinline__ size_t col_index(int plane, int nplanes, int y, int n
     return (((size_t)d * nplanes + plane) * ny + yy) * N;
 }
 
-template <int N, int CZ, int S>
+template <int N, int CZ, int S, bool SLAB>
 __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const float2* __restrict__ in,
                                                                      float2* __restrict__ out, int in_ny, int out_ny,
                                                                      const float2* __restrict__ tw) {
@@ -527,12 +546,24 @@ __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const floa
     const int plane = blockIdx.y, nplanes = gridDim.y;
     const size_t zc = (size_t)blockIdx.x * CZ + col;
     float2 v[P];
+    if constexpr (SLAB) {
 #pragma unroll
-    for (int q = 0; q < P; ++q) v[q] = in[col_index(plane, nplanes, t + T * q, in_ny, N) + zc];
+        for (int q = 0; q < P; ++q) v[q] = in[col_index(plane, nplanes, t + T * q, in_ny, N) + zc];
+    } else {
+        const float2* p = in + ((size_t)plane * N + t) * N + zc;     // one 64-bit base, 32-bit constant offsets
+#pragma unroll
+        for (int q = 0; q < P; ++q) v[q] = p[(unsigned)(T * q) * (unsigned)N];
+    }
     ColLayout<CZ> sl{col};
     fft_regs<N, P, C::R1, C::R2, C::R3, S>(v, t, sm, sl, tw);
+    if constexpr (SLAB) {
 #pragma unroll
-    for (int q = 0; q < P; ++q) out[col_index(plane, nplanes, t + T * q, out_ny, N) + zc] = v[q];
+        for (int q = 0; q < P; ++q) out[col_index(plane, nplanes, t + T * q, out_ny, N) + zc] = v[q];
+    } else {
+        float2* p = out + ((size_t)plane * N + t) * N + zc;
+#pragma unroll
+        for (int q = 0; q < P; ++q) p[(unsigned)(T * q) * (unsigned)N] = v[q];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -580,11 +611,13 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     float2 v[P];
     // each plane element is read from HBM once; the mirrored partner X[M-k] comes from the tile
     // parked in shared memory (plane M, the partner of k = 0, is outside the tile)
+    {
+        const float2* pl = src + (size_t)t * A.ncols;
+        const size_t lstride = (size_t)T * A.ncols;
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        v[q] = src[(size_t)(t + T * q) * A.ncols];
-        sm[sl(t + T * q)] = v[q];
+        for (int q = 0; q < P; ++q, pl += lstride) v[q] = *pl;
     }
+    fft_store_natural<M, P>(v, t, sm, sl);
     float2 xnyq = make_float2(0.f, 0.f);
     if (t == 0) xnyq = src[(size_t)M * A.ncols];
     __syncthreads();
@@ -600,12 +633,12 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     }
     if constexpr (C::R2 > 1) __syncthreads();          // the exchanges reuse the buffer
     fft_regs<M, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, A.tw);
-    float* dst = A.field + g;
+    float* dst = A.field + g + (size_t)(2 * t) * A.ncols;       // rows 2m, 2m+1 of m = t + T*q
+    const size_t sstride = (size_t)(2 * T) * A.ncols;
     const bool do_exp = (A.flags & FB_F_EXP) != 0;
     float acc = 0.f, acc2 = 0.f;
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int m = t + T * q;
+    for (int q = 0; q < P; ++q, dst += sstride) {
         float r0 = v[q].x * A.scale, r1 = v[q].y * A.scale;
         if (do_exp) {
             r0 = expf(r0);
@@ -613,8 +646,8 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
         }
         acc += r0 + r1;
         acc2 = fmaf(r0, r0, fmaf(r1, r1, acc2));
-        dst[(size_t)(2 * m) * A.ncols] = r0;
-        dst[(size_t)(2 * m + 1) * A.ncols] = r1;
+        dst[0] = r0;
+        dst[A.ncols] = r1;
     }
     if (A.sums) {
         double s1 = warp_sum((double)acc), s2 = warp_sum((double)acc2);
@@ -652,18 +685,15 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
     const size_t g = (size_t)blockIdx.x * CZ + col;
-    const float* src = A.field_in + g;
+    const float* src = A.field_in + g + (size_t)(2 * t) * A.ncols;
+    const size_t lstride = (size_t)(2 * T) * A.ncols;
     float2 v[P];
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int m = t + T * q;
-        v[q] = make_float2(src[(size_t)(2 * m) * A.ncols], src[(size_t)(2 * m + 1) * A.ncols]);
-    }
+    for (int q = 0; q < P; ++q, src += lstride) v[q] = make_float2(src[0], src[A.ncols]);
     ColLayout<CZ> sl{col};
     fft_regs<M, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, A.tw);
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];
+    fft_store_natural<M, P>(v, t, sm, sl);
     __syncthreads();
     float2* dst = A.spec_out + g;
 #pragma unroll

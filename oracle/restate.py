@@ -485,23 +485,26 @@ def philox4x32(ctr, key):
     return np.stack(c, axis=-1)
 
 
-def philox_normals(seed, index):
+def philox_normals(seed, index, N):
     """
-    Two N(0,1) per cell: (re, im) of the white noise W at global linear cell
-    ``index`` (uint64 array).  One Philox block (counter = index // 2) serves two
-    cells: words (0,1) -> even cell, words (2,3) -> odd cell.
-    u1 = (x0 + 0.5) 2^-32, u2 = (x1 + 0.5) 2^-32,
-    r = sqrt(-2 ln u1), re = r cos(2 pi u2), im = r sin(2 pi u2).
+    Two N(0,1) per cell: (re, im) of the white noise W at global linear cell ``index``
+    (uint64 array, index = (a N + b) N + c) of an N^3 grid.  One Philox block serves the conjugate
+    pair of modes k, -k: counter = min(index(k), index(-k)); the cell with the smaller index takes
+    words (0,1), the other words (2,3).
+    u1 = (x0 + 0.5) 2^-32, u2 = (x1 + 0.5) 2^-32, r = sqrt(-2 ln u1), re = r cos(2 pi u2), im = r sin(2 pi u2).
     """
     index = np.asarray(index, dtype=np.uint64)
-    blk = index >> np.uint64(1)
-    odd = (index & np.uint64(1)).astype(bool)
+    n = np.uint64(N)
+    a, b, c = index // (n * n), (index // n) % n, index % n
+    mirror = (((n - a) % n) * n + (n - b) % n) * n + (n - c) % n
+    blk = np.minimum(index, mirror)
+    second = index > mirror
     ctr = np.zeros(index.shape + (4,), dtype=np.uint32)
     ctr[..., 0] = (blk & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     ctr[..., 1] = (blk >> np.uint64(32)).astype(np.uint32)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
     x = philox4x32(ctr, key)
-    u1 = (np.where(odd, x[..., 2], x[..., 0]).astype(np.float64) + 0.5) * 2.0 ** -32
-    u2 = (np.where(odd, x[..., 3], x[..., 1]).astype(np.float64) + 0.5) * 2.0 ** -32
+    u1 = (np.where(second, x[..., 2], x[..., 0]).astype(np.float64) + 0.5) * 2.0 ** -32
+    u2 = (np.where(second, x[..., 3], x[..., 1]).astype(np.float64) + 0.5) * 2.0 ** -32
     r = np.sqrt(-2.0 * np.log(u1))
     return r * np.cos(TWO_PI * u2), r * np.sin(TWO_PI * u2)

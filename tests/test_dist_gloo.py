@@ -51,7 +51,7 @@ class NumpyEngine(object):
 
     def realise_kspace(self, seed, flags, want_pk):
         idx = np.arange(N ** 3, dtype=np.uint64).reshape(N, N, N)
-        re, im = R.philox_normals(seed, idx)                      # every rank can evaluate any cell
+        re, im = R.philox_normals(seed, idx, N)                      # every rank can evaluate any cell
         half = R.hermitian_half_from_noise(re, im, R.sqrt_pk_half(self.pkf, N, *L))
         local = half[self.a0:self.a0 + self.na]
         work = np.fft.ifft(np.fft.ifft(local, axis=2), axis=1) * N * N       # z rows, y columns (unnormalised)
@@ -104,7 +104,7 @@ def test_two_rank_realise_matches_single_process(tmp_path, world):
     s.close()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     idx = np.arange(N ** 3, dtype=np.uint64).reshape(N, N, N)
-    re, im = R.philox_normals(SEED, idx)
+    re, im = R.philox_normals(SEED, idx, N)
     _, pkf = pk_function(0.5)
     ref, half = R.realise_density_lean(re, im, pkf, N, *L)
     full = np.empty((N, N, N))

@@ -167,7 +167,7 @@ def test_philox_noise_matches_oracle(gpu):
     field = np.empty((N, N, N), np.float32)
     plan.realise(None, None, seed=0x1234567890ABCDEF, field_out=field)
     idx = np.arange(N ** 3, dtype=np.uint64).reshape(N, N, N)
-    re, im = R.philox_normals(0x1234567890ABCDEF, idx)
+    re, im = R.philox_normals(0x1234567890ABCDEF, idx, N)
     ref, _ = R.realise_density_lean(re, im, pkf, N, *L)
     assert rel_l2(field, ref) < TOL
     plan.close()

@@ -147,5 +147,5 @@ def test_philox_known_answer():
     ctr = np.full((1, 4), 0xffffffff, np.uint32)
     out = R.philox4x32(ctr, np.full(2, 0xffffffff, np.uint32))
     assert [hex(int(x)) for x in out[0]] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
-    re, im = R.philox_normals(42, np.arange(200000))
+    re, im = R.philox_normals(42, np.arange(64 ** 3), 64)
     assert abs(re.mean()) < 0.01 and abs(re.std() - 1) < 0.01 and abs(np.corrcoef(re, im)[0, 1]) < 0.01
