@@ -326,13 +326,20 @@ int fb_device_info(int device, char* name, int name_len, int* sm_count, size_t* 
     return 0;
 }
 
-static int upload_table(float** slot, const float* host, size_t n) {
-    if (*slot) {
-        FB_CUDA(cudaFree(*slot));
+static int upload_table(float** slot, size_t* cap, const float* host, size_t n) {
+    if (!host) {
+        if (*slot) FB_CUDA(cudaFree(*slot));
         *slot = nullptr;
+        *cap = 0;
+        return 0;
     }
-    if (!host) return 0;
-    FB_CUDA(cudaMalloc((void**)slot, n * sizeof(float)));
+    if (*cap < n) {                                  // reuse the allocation when the table fits
+        if (*slot) FB_CUDA(cudaFree(*slot));
+        *slot = nullptr;
+        *cap = 0;
+        FB_CUDA(cudaMalloc((void**)slot, n * sizeof(float)));
+        *cap = n;
+    }
     FB_CUDA(cudaMemcpy(*slot, host, n * sizeof(float), cudaMemcpyDefault));
     return 0;
 }
@@ -346,7 +353,7 @@ int fb_set_sqrt_pk(fb_plan* p, const float* table, long n, int mode, double log2
     } else {
         FB_CHECK(n >= 2 && dlog2s > 0, "fb_set_sqrt_pk: log table needs n>=2 and dlog2s>0");
     }
-    if (upload_table(&p->sqrtp, table, (size_t)n)) return -2;
+    if (upload_table(&p->sqrtp, &p->tab_cap[0], table, (size_t)n)) return -2;
     p->sqrtp_mode = mode;
     p->sqrtp_n = n;
     p->log2s0 = log2s0;
@@ -358,9 +365,9 @@ int fb_set_filter(fb_plan* p, const float* tperp, const float* tpar, const float
     FB_CUDA(cudaStreamSynchronize(p->stream));
     const size_t N = p->N, H = p->N / 2 + 1;
     FB_CHECK((tperp == nullptr) == (tpar == nullptr), "fb_set_filter: tperp and tpar go together");
-    if (upload_table(&p->tperp, tperp, H * N)) return -2;
-    if (upload_table(&p->tpar, tpar, N)) return -2;
-    if (upload_table(&p->tdense, tdense, H * N * N)) return -2;
+    if (upload_table(&p->tperp, &p->tab_cap[1], tperp, H * N)) return -2;
+    if (upload_table(&p->tpar, &p->tab_cap[2], tpar, N)) return -2;
+    if (upload_table(&p->tdense, &p->tab_cap[3], tdense, H * N * N)) return -2;
     return 0;
 }
 

@@ -99,6 +99,7 @@ struct fb_plan {
     long sqrtp_n;
     double log2s0, dlog2s;
     float *tperp, *tpar, *tdense;
+    size_t tab_cap[4];
     // workspaces
     float2* work;           // [(na)][N][N] complex
     size_t work_bytes;
