@@ -105,7 +105,7 @@ static int launch_x(fb_plan* p, const XArgs& a, bool inv) {
         case 256: return launch_x_n<256>(p, a, inv, 32);
         case 512: return launch_x_n<512>(p, a, inv, 16);
         case 1024: return launch_x_n<1024>(p, a, inv, 16);
-        case 2048: return launch_x_n<2048>(p, a, inv, 8);
+        case 2048: return launch_x_n<2048>(p, a, inv, 16);
         default: set_error("unsupported N=%d", p->N); return -1;
     }
 }
