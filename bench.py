@@ -295,13 +295,19 @@ def run_multi(args, rank, world, local_rank):
     N = args.size_multi
     L = 2000.0 * N / 1024.0
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")       # NCCL kernels must not queue behind our grids
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-    eng = fbd.CudaEngine(N, (L, L, L), rank, world, local_rank)
+    chunks = int(os.environ.get("FB_CHUNKS", "4"))
+    while chunks > 1 and ((N // 2) // world) % chunks:
+        chunks //= 2
+    eng = fbd.CudaEngine(N, (L, L, L), rank, world, local_rank, chunks=chunks)
     configure_plan(eng.plan, N, L)
     dr = fbd.DistributedRealiser(eng)
     flags = _lib.F_SQRTPK | _lib.F_FILTER
 
     def step(seed):
+        if chunks > 1:
+            return dr.realise_overlapped(seed, flags, want_pk=True)
         return dr.realise(seed, flags, want_pk=True)
 
     for w in range(args.warmup):
@@ -317,34 +323,51 @@ def run_multi(args, rank, world, local_rank):
         # events on torch's stream bracket all device work of the steps
         ev0.record()
         for s in range(args.steps):
-            eng.realise_kspace(s, flags, True)
-            eng.sync()
-            xev[s][0].record()
-            dr.exchange()
-            xev[s][1].record()
-            eng.sync_exchange()
-            eng.x_to_real()
-            eng.sync()
+            if chunks > 1:
+                step(s)
+                eng.sync()
+            else:
+                eng.realise_kspace(s, flags, True)
+                eng.sync()
+                xev[s][0].record()
+                dr.exchange()
+                xev[s][1].record()
+                eng.sync_exchange()
+                eng.x_to_real()
+                eng.sync()
         ev1.record()
         torch.cuda.synchronize()
     t_wall = ev0.elapsed_time(ev1) * 1e-3
-    t_x = sum(a.elapsed_time(b) for a, b in xev) * 1e-3
+    # the exchange alone (whole half spectrum, not overlapped), for the NVLink roofline
+    xs = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record()
+        dr.exchange()
+        b.record()
+        torch.cuda.synchronize()
+        xs.append(a.elapsed_time(b) * 1e-3)
+    t_x_alone = min(xs)
+    t_x = sum(a.elapsed_time(b) for a, b in xev) * 1e-3 if chunks == 1 else 0.0
     dist.barrier()
-    t = torch.tensor([t_wall, t_x], device="cuda", dtype=torch.float64)
+    t = torch.tensor([t_wall, t_x, t_x_alone], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_wall, t_x = float(t[0]), float(t[1])
+    t_wall, t_x, t_x_alone = float(t[0]), float(t[1]), float(t[2])
     launches = _lib.launch_count() - launches0
     if rank == 0:
         ms_step = t_wall / args.steps * 1e3
         value = N ** 3 / (ms_step * 1e-3) / 1e6
         hbm_peak, peak_src = measured_peaks()
         a2a = max(fbd.alltoall_bytes_per_rank(N, world))
-        nv = a2a / (t_x / args.steps) / 1e9 if t_x > 0 else None
+        nv = a2a / t_x_alone / 1e9
         line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "%d^3 realise + filter + binned P(k), Philox noise, slab decomposition over "
-                                       "%d GPUs, one NCCL all-to-all" % (N, world), "box_Mpc": L,
+                                       "%d GPUs, one NCCL all-to-all in %d chunks overlapped with the k-space passes" % (N, world, chunks),
+                           "box_Mpc": L,
                            "l2": "per-GPU working set %.1f GB >> L2" % (12.0 * N ** 3 / world / 1e9)},
                 "clocks": clk.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": value, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step":
@@ -354,7 +377,7 @@ def run_multi(args, rank, world, local_rank):
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": BYTES_PER_CELL_PHILOX * N ** 3 / world / (ms_step * 1e-3) / 1e9 / hbm_peak,
                              "traffic": None, "peak_source": peak_src,
-                             "nvlink": {"bytes_sent_per_gpu": a2a, "exchange_ms": t_x / args.steps * 1e3,
+                             "nvlink": {"bytes_sent_per_gpu": a2a, "exchange_ms": t_x_alone * 1e3, "overlapped_chunks": chunks,
                                         "achieved_GBs": nv, "frac_of_900": None if nv is None else nv / 900.0,
                                         "frac_of_measured_770": None if nv is None else nv / 770.0}},
                 "cpu_baseline": None}

@@ -63,6 +63,7 @@ SIGNATURES = {
     "fb_halo_counts": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
+    "fb_fft_pass_x_c2r_gather": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_r2c": (_i, [_vp, _vp, _vp, _l]),
     "fb_realise_local_kspace": (_i, [_vp, _u64, _i, _vp, _vp, _i, C.POINTER(PkResult)]),
     "fb_forward_local_kspace": (_i, [_vp, _vp, _vp, _i, _vp, _i, C.POINTER(PkResult)]),
@@ -297,6 +298,12 @@ class Plan(object):
     def fft_pass_x_c2r(self, spec, field, ncols, flags=0, scale=1.0):
         sums = (C.c_double * 2)()
         check(self.lib.fb_fft_pass_x_c2r(self.h, _ptr(spec), _ptr(field), int(ncols), int(flags), float(scale), sums))
+        return sums[0], sums[1]
+
+    def fft_pass_x_c2r_gather(self, spec, plane_off, field, ncols, flags=0, scale=1.0):
+        sums = (C.c_double * 2)()
+        check(self.lib.fb_fft_pass_x_c2r_gather(self.h, _ptr(spec), _ptr(plane_off), _ptr(field), int(ncols),
+                                                int(flags), float(scale), sums))
         return sums[0], sums[1]
 
     def fft_pass_x_r2c(self, field, spec, ncols):

@@ -623,11 +623,13 @@ int fb_fft_pass_c2c(fb_plan* p, void* data, int nplanes, int pass, int sign) {
     return launch_rows_fwd(p, ra);
 }
 
-int fb_fft_pass_x_c2r(fb_plan* p, const void* spec, float* field, long ncols, int flags, float scale, double* sum_out) {
+static int x_c2r_impl(fb_plan* p, const void* spec, const long* plane_off, float* field, long ncols, int flags,
+                      float scale, double* sum_out) {
     FB_CUDA(cudaSetDevice(p->device));
     FB_CHECK(is_device_ptr(spec) && is_device_ptr(field), "fb_fft_pass_x_c2r: buffers must be device memory");
     XArgs xa;
     memset(&xa, 0, sizeof(xa));
+    xa.plane_off = plane_off;
     xa.spec = (const float2*)spec;
     xa.field = field;
     xa.tw = p->tw;
@@ -638,6 +640,16 @@ int fb_fft_pass_x_c2r(fb_plan* p, const void* spec, float* field, long ncols, in
     if (scal_clear(p)) return -2;
     if (launch_x_c2r(p, xa)) return -3;
     return scal_fetch(p, sum_out, 2);
+}
+
+int fb_fft_pass_x_c2r(fb_plan* p, const void* spec, float* field, long ncols, int flags, float scale, double* sum_out) {
+    return x_c2r_impl(p, spec, nullptr, field, ncols, flags, scale, sum_out);
+}
+
+int fb_fft_pass_x_c2r_gather(fb_plan* p, const void* spec, const long* plane_off, float* field, long ncols, int flags,
+                             float scale, double* sum_out) {
+    FB_CHECK(plane_off != nullptr && is_device_ptr(plane_off), "fb_fft_pass_x_c2r_gather: plane_off must be device memory");
+    return x_c2r_impl(p, spec, plane_off, field, ncols, flags, scale, sum_out);
 }
 
 int fb_fft_pass_x_r2c(fb_plan* p, const float* field, void* spec, long ncols) {

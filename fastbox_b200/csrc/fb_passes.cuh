@@ -576,6 +576,7 @@ __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const floa
 // grid = ncols/CZ, block = CZ*T(M)
 // ---------------------------------------------------------------------------
 struct XArgs {
+    const long* plane_off;  // optional: element offset of each kx plane (chunked exchange buffers)
     const float2* spec;
     float* field;
     const float* field_in;
@@ -611,7 +612,10 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     float2 v[P];
     // each plane element is read from HBM once; the mirrored partner X[M-k] comes from the tile
     // parked in shared memory (plane M, the partner of k = 0, is outside the tile)
-    {
+    if (A.plane_off) {                                 // planes gathered from several receive buffers
+#pragma unroll
+        for (int q = 0; q < P; ++q) v[q] = src[__ldg(&A.plane_off[t + T * q])];
+    } else {
         const float2* pl = src + (size_t)t * A.ncols;
         const size_t lstride = (size_t)T * A.ncols;
 #pragma unroll
@@ -619,7 +623,7 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     }
     fft_store_natural<M, P>(v, t, sm, sl);
     float2 xnyq = make_float2(0.f, 0.f);
-    if (t == 0) xnyq = src[(size_t)M * A.ncols];
+    if (t == 0) xnyq = A.plane_off ? src[__ldg(&A.plane_off[M])] : src[(size_t)M * A.ncols];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < P; ++q) {

@@ -46,13 +46,49 @@ def alltoall_bytes_per_rank(N, world):
     return [8 * na * ny * N * (world - 1) for na in plane_counts(N, world)]
 
 
+def chunk_planes(N, world, rank, chunks):
+    """[(first global plane, count)] for each exchange chunk of this rank (Nyquist plane in the last)."""
+    a0, na, _, _ = slab_geometry(N, world, rank)
+    per = (N // 2) // world
+    if chunks < 1 or per % chunks != 0:
+        raise ValueError("chunks=%d must divide the %d planes per rank" % (chunks, per))
+    nc = per // chunks
+    out = [(a0 + c * nc, nc) for c in range(chunks)]
+    if rank == world - 1:
+        out[-1] = (out[-1][0], nc + 1)
+    return out
+
+
+def recv_regions(N, world, chunks):
+    """Plane offset of each chunk's region in the receive buffer, and planes per (chunk, source)."""
+    counts = [[chunk_planes(N, world, s, chunks)[c][1] for s in range(world)] for c in range(chunks)]
+    starts = np.concatenate([[0], np.cumsum([sum(row) for row in counts])])
+    return starts[:-1].astype(np.int64), counts
+
+
+def plane_offsets(N, world, chunks, ny):
+    """
+    Element offset (in complex64 units) of every global kx plane a = 0..N/2 inside the receive
+    buffer when the exchange is done chunk by chunk: region(chunk) -> source rank -> plane.
+    """
+    starts, counts = recv_regions(N, world, chunks)
+    off = np.empty(N // 2 + 1, dtype=np.int64)
+    for c in range(chunks):
+        pos = int(starts[c])
+        for s in range(world):
+            a_first, n = chunk_planes(N, world, s, chunks)[c]
+            off[a_first:a_first + n] = (pos + np.arange(n)) * ny * N
+            pos += n
+    return off
+
+
 class CudaEngine(object):
     """Local passes on one GPU through libfastbox_b200 (torch tensors carry the buffers)."""
 
-    def __init__(self, N, L, rank, world, device):
+    def __init__(self, N, L, rank, world, device, chunks=1):
         import torch
         self.torch = torch
-        self.N, self.rank, self.world = N, rank, world
+        self.N, self.rank, self.world, self.chunks = N, rank, world, chunks
         self.a0, self.na, self.y0, self.ny = slab_geometry(N, world, rank)
         self.dev = torch.device("cuda", device)
         self.plan = _lib.Plan(N, L[0], L[1], L[2], device)
@@ -62,6 +98,24 @@ class CudaEngine(object):
         self.send = torch.empty((world, self.na, self.ny, N), dtype=c64, device=self.dev)
         self.recv = torch.empty((N // 2 + 1, self.ny, N), dtype=c64, device=self.dev)
         self.field = torch.empty((N, self.ny, N), dtype=torch.float32, device=self.dev)
+        if chunks > 1:
+            self.my_chunks = chunk_planes(N, world, rank, chunks)
+            self.send_c = [torch.empty((world, n, self.ny, N), dtype=c64, device=self.dev) for _, n in self.my_chunks]
+            self.plane_off = torch.from_numpy(plane_offsets(N, world, chunks, self.ny)).to(self.dev)
+
+    def realise_kspace_chunk(self, c, seed, flags, want_pk):
+        """Same as realise_kspace for exchange chunk c only (fills ``self.send_c[c]``)."""
+        a_first, n = self.my_chunks[c]
+        self.plan.set_slab(a_first, n, self.y0, self.ny)
+        try:
+            return self.plan.realise_local_kspace(seed, flags, self.work, self.send_c[c], self.ny, want_pk=want_pk)
+        finally:
+            self.plan.set_slab(self.a0, self.na, self.y0, self.ny)
+
+    def x_to_real_gather(self, flags=0, scale=1.0):
+        N = self.N
+        return self.plan.fft_pass_x_c2r_gather(self.recv, self.plane_off, self.field, self.ny * N, flags=flags,
+                                               scale=scale / float(N) ** 3)
 
     def realise_kspace(self, seed, flags, want_pk):
         """rows + columns on the local planes; fills ``self.send``; returns local P(k) moments."""
@@ -98,6 +152,9 @@ class DistributedRealiser(object):
         ny = engine.ny
         self.in_splits = [engine.na * ny * N] * world                 # elements sent to each peer
         self.out_splits = [na * ny * N for na in plane_counts(N, world)]
+        self.chunks = getattr(engine, "chunks", 1)
+        if self.chunks > 1:
+            self.region_start, self.region_counts = recv_regions(N, world, self.chunks)
 
     def exchange(self):
         e = self.e
@@ -107,6 +164,52 @@ class DistributedRealiser(object):
         self.dist.all_to_all_single(e.recv.reshape(-1), e.send.reshape(-1),
                                     output_split_sizes=self.out_splits, input_split_sizes=self.in_splits,
                                     group=self.group)
+
+    def exchange_chunk(self, c):
+        """Asynchronous all-to-all of chunk c into its region of the receive buffer."""
+        e = self.e
+        N, ny = e.N, e.ny
+        n_mine = e.my_chunks[c][1]
+        counts = self.region_counts[c]
+        start = int(self.region_start[c]) * ny * N
+        total = sum(counts) * ny * N
+        out = e.recv.reshape(-1)[start:start + total]
+        if e.world == 1:
+            out.copy_(e.send_c[c].reshape(-1))
+            return None
+        return self.dist.all_to_all_single(out, e.send_c[c].reshape(-1),
+                                           output_split_sizes=[n * ny * N for n in counts],
+                                           input_split_sizes=[n_mine * ny * N] * e.world, group=self.group,
+                                           async_op=True)
+
+    def realise_overlapped(self, seed, flags, want_pk=False, scale=1.0):
+        """
+        Chunked pipeline: the all-to-all of chunk c runs (NCCL stream) while the z/y passes of chunk
+        c+1 run on the library stream; the x pass gathers the planes through ``plane_off``.
+        """
+        e = self.e
+        pending, acc = [], None
+        for c in range(self.chunks):
+            res = e.realise_kspace_chunk(c, seed, flags, want_pk)
+            e.sync()
+            pending.append(self.exchange_chunk(c))
+            if want_pk:
+                acc = res if acc is None else {k: acc[k] + res[k] for k in ("count", "sum1", "sum2")}
+        for w in pending:
+            if w is not None:
+                w.wait()
+        e.sync_exchange()
+        sums = e.x_to_real_gather(flags=flags & _lib.F_EXP, scale=scale)
+        return e.field, self._reduce_moments(acc) if want_pk else None, sums
+
+    def _reduce_moments(self, res):
+        e = self.e
+        t = e.moments_tensor(res)
+        if e.world > 1:
+            self.dist.all_reduce(t, group=self.group)
+        arr = t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
+        n = arr.size // 3
+        return dict(count=np.rint(arr[:n]).astype(np.uint64), sum1=arr[n:2 * n], sum2=arr[2 * n:])
 
     def realise(self, seed, flags, want_pk=False, scale=1.0):
         """
@@ -120,12 +223,5 @@ class DistributedRealiser(object):
         self.exchange()
         e.sync_exchange()
         sums = e.x_to_real(flags=flags & _lib.F_EXP, scale=scale)
-        pk = None
-        if want_pk:
-            t = e.moments_tensor(res)
-            if e.world > 1:
-                self.dist.all_reduce(t, group=self.group)
-            arr = t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
-            n = arr.size // 3
-            pk = dict(count=np.rint(arr[:n]).astype(np.uint64), sum1=arr[n:2 * n], sum2=arr[2 * n:])
+        pk = self._reduce_moments(res) if want_pk else None
         return e.field, pk, sums

@@ -165,6 +165,10 @@ int fb_fft_pass_c2c(fb_plan* plan, void* data, int nplanes, int pass, int sign);
 /* x pass, real <-> half complex over planes; ncols = columns per plane.        */
 int fb_fft_pass_x_c2r(fb_plan* plan, const void* spec, float* field, long ncols, int flags, float scale,
                       double* sum_out);
+/* same, with the kx planes gathered through plane_off[k] (device array of N/2+1 element offsets
+ * relative to `spec`): lets the all-to-all be issued in chunks that overlap the k-space passes. */
+int fb_fft_pass_x_c2r_gather(fb_plan* plan, const void* spec, const long* plane_off, float* field, long ncols,
+                             int flags, float scale, double* sum_out);
 int fb_fft_pass_x_r2c(fb_plan* plan, const float* field, void* spec, long ncols);
 /* Slab-decomposed (multi-GPU) halves of the pipelines; the all-to-all between them is done by
  * the caller (torch.distributed / NCCL, fastbox_b200/dist.py).  `ny` = y rows per rank.

@@ -32,22 +32,48 @@ def test_slab_geometry_covers_everything():
     with pytest.raises(ValueError):
         fbd.slab_geometry(16, 3, 0)
     assert fbd.alltoall_bytes_per_rank(2048, 8)[0] == 8 * 128 * 256 * 2048 * 7
+    # chunked exchange: every plane lands exactly once in the receive buffer
+    for n, w, c in [(32, 2, 4), (64, 4, 2), (2048, 8, 4)]:
+        off = fbd.plane_offsets(n, w, c, n // w)
+        assert np.array_equal(np.sort(off), np.arange(n // 2 + 1) * (n // w) * n)
+        assert sum(cnt for r in range(w) for _, cnt in fbd.chunk_planes(n, w, r, c)) == n // 2 + 1
+    with pytest.raises(ValueError):
+        fbd.chunk_planes(32, 2, 0, 3)
 
 
 class NumpyEngine(object):
     """Same interface as dist.CudaEngine, NumPy float64 arithmetic from oracle/restate.py."""
 
-    def __init__(self, rank, world):
+    def __init__(self, rank, world, chunks=1):
         import torch
         self.torch = torch
-        self.N, self.rank, self.world = N, rank, world
+        self.N, self.rank, self.world, self.chunks = N, rank, world, chunks
         self.a0, self.na, self.y0, self.ny = fbd.slab_geometry(N, world, rank)
         self.send = torch.empty((world, self.na, self.ny, N), dtype=torch.complex128)
         self.recv = torch.empty((N // 2 + 1, self.ny, N), dtype=torch.complex128)
         self.field = None
+        if chunks > 1:
+            self.my_chunks = fbd.chunk_planes(N, world, rank, chunks)
+            self.send_c = [torch.empty((world, n, self.ny, N), dtype=torch.complex128) for _, n in self.my_chunks]
+            self.plane_off = fbd.plane_offsets(N, world, chunks, self.ny)
         self.nedges = 20
         _, self.pkf = pk_function(0.5)
         self.edges = R.pk_bin_edges(N, *L, nbins=self.nedges)
+
+    def realise_kspace_chunk(self, c, seed, flags, want_pk):
+        a_first, n = self.my_chunks[c]
+        saved = (self.a0, self.na, self.send)
+        self.a0, self.na, self.send = a_first, n, self.send_c[c]
+        try:
+            return self.realise_kspace(seed, flags, want_pk)
+        finally:
+            self.a0, self.na, self.send = saved
+
+    def x_to_real_gather(self, flags=0, scale=1.0):
+        flat = self.recv.numpy().reshape(-1)
+        planes = np.stack([flat[o:o + self.ny * N].reshape(self.ny, N) for o in self.plane_off])
+        self.field = np.fft.irfft(planes, n=N, axis=0) * N * scale / float(N) ** 3
+        return (float(self.field.sum()), float((self.field ** 2).sum()))
 
     def realise_kspace(self, seed, flags, want_pk):
         idx = np.arange(N ** 3, dtype=np.uint64).reshape(N, N, N)
@@ -83,26 +109,29 @@ class NumpyEngine(object):
                                                      res["sum2"][:n]]))
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, chunks):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    eng = NumpyEngine(rank, world)
+    eng = NumpyEngine(rank, world, chunks)
     dr = fbd.DistributedRealiser(eng)
-    field, pk, sums = dr.realise(SEED, _lib.F_SQRTPK, want_pk=True)
+    if chunks > 1:
+        field, pk, sums = dr.realise_overlapped(SEED, _lib.F_SQRTPK, want_pk=True)
+    else:
+        field, pk, sums = dr.realise(SEED, _lib.F_SQRTPK, want_pk=True)
     np.savez(os.path.join(outdir, "r%d.npz" % rank), field=eng.field, y0=eng.y0, **pk)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_two_rank_realise_matches_single_process(tmp_path, world):
+@pytest.mark.parametrize("world,chunks", [(2, 1), (2, 2)])
+def test_two_rank_realise_matches_single_process(tmp_path, world, chunks):
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), chunks), nprocs=world, join=True)
     idx = np.arange(N ** 3, dtype=np.uint64).reshape(N, N, N)
     re, im = R.philox_normals(SEED, idx, N)
     _, pkf = pk_function(0.5)

@@ -81,3 +81,27 @@ def test_two_slabs_emulated_on_one_gpu(gpu):
     assert np.array_equal(cnt, res_ref["count"].astype(np.int64))
     s1 = sum(m["sum1"] for m in moments)
     assert np.allclose(s1, res_ref["sum1"], rtol=1e-12)
+
+
+def test_chunked_pipeline_world1(gpu):
+    """Chunked (overlap-capable) pipeline with the gathered x pass == fused single call."""
+    import torch
+    from fastbox_b200 import kspace as ks
+    from oracle import restate as R
+    from _util import pk_function
+    N, L = 64, (1e3, 1e3, 1e3)
+    flags = _lib.F_SQRTPK
+    plan, edges = setup_plan(N, L, 0.8, nbins=20)
+    ref = np.empty((N, N, N), np.float32)
+    res_ref, _ = plan.realise(None, None, seed=3, flags=flags, field_out=ref, want_pk=True)
+    plan.close()
+    _, pkf = pk_function(0.8)
+    eng = fbd.CudaEngine(N, L, 0, 1, 0, chunks=4)
+    eng.plan.set_sqrt_pk(ks.sqrt_pk_int_lut(pkf, N, L[0], R.boxfactor(N, *L)), 1)
+    eng.plan.set_pk_bins(ks.bin_thresholds(edges))
+    dr = fbd.DistributedRealiser(eng)
+    field, pk, sums = dr.realise_overlapped(3, flags, want_pk=True)
+    torch.cuda.synchronize()
+    assert rel_l2(field.cpu().numpy().reshape(N, N, N), ref.astype(np.float64)) < 1e-6
+    assert np.array_equal(pk["count"], res_ref["count"])
+    assert np.allclose(pk["sum1"], res_ref["sum1"], rtol=1e-12)

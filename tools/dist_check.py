@@ -33,11 +33,15 @@ def main():
     ok = True
     for N in (64, 256):
         L = 2000.0 * N / 1024
-        eng = fbd.CudaEngine(N, (L, L, L), rank, world, lr)
+        chunks = 2 if (N // 2) // world % 2 == 0 else 1
+        eng = fbd.CudaEngine(N, (L, L, L), rank, world, lr, chunks=chunks)
         tables(eng.plan, N, L)
         dr = fbd.DistributedRealiser(eng)
         flags = _lib.F_SQRTPK | _lib.F_FILTER
-        field, pk, sums = dr.realise(7, flags, want_pk=True)
+        if chunks > 1:
+            field, pk, sums = dr.realise_overlapped(7, flags, want_pk=True)
+        else:
+            field, pk, sums = dr.realise(7, flags, want_pk=True)
         torch.cuda.synchronize()
         gathered = [torch.empty_like(field) for _ in range(world)]
         dist.all_gather(gathered, field)
