@@ -50,6 +50,16 @@ struct RowsArgs {
 // are accumulated in registers and flushed once per thread).  The FFT itself works in
 // Stockham order (thread t owns t + T*q); one shared-memory transpose connects the two.
 // ---------------------------------------------------------------------------
+// streaming variant: read-once bulk data (noise cubes) must not evict the k-space tables from L1
+template <int P>
+__device__ __forceinline__ void load_run_stream(const float* __restrict__ p, float (&out)[P]) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < P / 4; ++i) {
+        const float4 v = __ldcs(p4 + i);
+        out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+    }
+}
 template <int P>
 __device__ __forceinline__ void load_run(const float* __restrict__ p, float (&out)[P]) {
     const float4* p4 = reinterpret_cast<const float4*>(p);
@@ -376,10 +386,10 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
             float2 g[4], mm[4], gm0;
             if constexpr (SRC == SRC_NOISE) {
                 float r[4], i[4], rm[4], im[4];
-                load_run<4>(A.re + row_g + cq, r);
-                load_run<4>(A.im + row_g + cq, i);
-                load_run<4>(A.re + row_m + mq, rm);
-                load_run<4>(A.im + row_m + mq, im);
+                load_run_stream<4>(A.re + row_g + cq, r);
+                load_run_stream<4>(A.im + row_g + cq, i);
+                load_run_stream<4>(A.re + row_m + mq, rm);
+                load_run_stream<4>(A.im + row_m + mq, im);
                 gm0 = make_float2(__ldg(&A.re[row_m + cm0]), __ldg(&A.im[row_m + cm0]));
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
