@@ -14,6 +14,30 @@ static int launch_cols_t(fb_plan* p, const float2* in, float2* out, int in_ny, i
     using G = ColGeom<N, CZ>;
     dim3 grid(N / CZ, nplanes);
     const bool slab = in_ny != 0 || out_ny != 0;
+    if constexpr (N >= 256) {
+        // persistent cp.async-pipelined kernel (two tile buffers).  Measured SLOWER than the plain kernel on
+        // B200 (2.25 ms vs 1.76 ms at 1024^3: 8-byte LDGSTS issue rate + one resident CTA), so it is
+        // opt-in (FB_COLS_PIPE=1) and kept as the starting point for a TMA-tiled version.
+        if (!slab && 2 * G::SMEM <= 220 * 1024 && env_int("FB_COLS_PIPE", 0)) {
+            const int ntiles = (N / CZ) * nplanes;
+            int per_sm = (int)((220 * 1024) / (2 * G::SMEM + 1024));
+            per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+            per_sm = env_int("FB_PIPE_CTAS", per_sm);
+            const int want = p->sm_count * per_sm;
+            const int ctas = want < ntiles ? want : ntiles;
+            if (sign < 0) {
+                auto kern = k_cols_c2c_pipe<N, CZ, -1>;
+                if (set_smem(kern, 2 * G::SMEM)) return -2;
+                kern<<<ctas, G::THREADS, 2 * G::SMEM, p->stream>>>(in, out, ntiles, p->tw);
+            } else {
+                auto kern = k_cols_c2c_pipe<N, CZ, +1>;
+                if (set_smem(kern, 2 * G::SMEM)) return -2;
+                kern<<<ctas, G::THREADS, 2 * G::SMEM, p->stream>>>(in, out, ntiles, p->tw);
+            }
+            FB_LAUNCH_CHECK();
+            return 0;
+        }
+    }
 #define FB_COLS_LAUNCH(SIGN_, SLAB_)                                                         \
     {                                                                                        \
         auto kern = k_cols_c2c<N, CZ, SIGN_, SLAB_>;                                         \

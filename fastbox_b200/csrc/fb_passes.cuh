@@ -7,6 +7,7 @@
 //     xc2r  (a -> x, stride = plane size; half-length complex FFT + real pre-processing)
 // Forward (P(k)) order is the mirror image: xr2c, cols, rows (+ histogram epilogue).
 #pragma once
+#include <cuda_pipeline.h>
 #include "fb_kspace.cuh"
 
 namespace fb {
@@ -573,6 +574,58 @@ __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const floa
         float2* p = out + ((size_t)plane * N + t) * N + zc;
 #pragma unroll
         for (int q = 0; q < P; ++q) p[(unsigned)(T * q) * (unsigned)N] = v[q];
+    }
+}
+
+// Persistent, software-pipelined variant of the y pass (plain layout): one CTA per SM loops over
+// tiles; while tile i is transformed, tile i+1 streams into the other shared-memory buffer with
+// cp.async (LDGSTS), so HBM never idles during the compute / exchange phases.  The landed tile is
+// transformed in place (its buffer doubles as the exchange buffer).
+template <int N, int CZ, int S>
+__global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS, (ColGeom<N, CZ>::THREADS <= 256 ? 3 : 1)) k_cols_c2c_pipe(const float2* __restrict__ in,
+                                                                             float2* __restrict__ out, int ntiles,
+                                                                             const float2* __restrict__ tw) {
+    using C = FftCfg<N>;
+    constexpr int P = C::P, T = C::T;
+    constexpr int TILE = (N + N / 16) * CZ;              // float2 elements per buffer
+    constexpr int PS = ColLayout<CZ>::pstride(T);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
+    ColLayout<CZ> sl{col};
+    const int p0 = sl(t);
+    constexpr int TPP = N / CZ;                          // tiles per plane
+    auto tile_ptr = [&](int tile) -> size_t {
+        const int plane = tile / TPP, zt = tile - plane * TPP;
+        return ((size_t)plane * N + t) * N + (size_t)zt * CZ + col;
+    };
+    auto prefetch = [&](int tile, float2* buf) {
+        const float2* g = in + tile_ptr(tile);
+#pragma unroll
+        for (int q = 0; q < P; ++q) __pipeline_memcpy_async(buf + p0 + q * PS, g + (size_t)(T * q) * N, sizeof(float2));
+        __pipeline_commit();
+    };
+    int tile = blockIdx.x;
+    int cur = 0;
+    if (tile < ntiles) prefetch(tile, sm);
+    for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+        float2* buf = sm + cur * TILE;
+        const int next = tile + gridDim.x;
+        if (next < ntiles) {
+            prefetch(next, sm + (cur ^ 1) * TILE);
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
+        }
+        float2 v[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) v[q] = buf[p0 + q * PS];      // own copies: visible after the wait
+        __syncthreads();                                           // everyone has its inputs before in-place exchanges
+        fft_regs<N, P, C::R1, C::R2, C::R3, S>(v, t, buf, sl, tw);
+        float2* g = out + tile_ptr(tile);
+#pragma unroll
+        for (int q = 0; q < P; ++q) g[(size_t)(T * q) * N] = v[q];
+        __syncthreads();                                           // buffer free before it is refilled
     }
 }
 
