@@ -1,7 +1,6 @@
-// fb_kspace.cuh -- per-mode k-space arithmetic fused into the first / last FFT pass:
-// sqrt(P) lookup (box.py:161-176), transfer function (box.py:374-378), velocity /
-// potential factors (box.py:254-274, 347), and the P(k) bin index + binned moments
-// (box.py:741-764).
+// fb_kspace.cuh -- per-mode k-space multipliers fused into the first FFT pass: sqrt(P) lookup
+// (box.py:161-176), transfer function (box.py:374-378), velocity / potential factors
+// (box.py:254-274, 347).  The P(k) binning (box.py:741-764) lives in fb_passes.cuh.
 #pragma once
 #include "fb_common.cuh"
 
@@ -55,85 +54,6 @@ __device__ __forceinline__ float k_amp(const KSpace& K, int flags, int kind, int
         amp *= comp * ik2;
     }
     return amp;
-}
-
-// ---- P(k) ------------------------------------------------------------------
-struct PkShared {
-    double thr[FB_MAX_EDGES];
-    double s1[FB_MAX_EDGES + 1], s2[FB_MAX_EDGES + 1], l2[FB_MAX_EDGES + 1], l4[FB_MAX_EDGES + 1];
-    unsigned long long cnt[FB_MAX_EDGES + 1];
-};
-
-__device__ __forceinline__ void pk_shared_init(PkShared& sh, const KSpace& K) {
-    for (int i = threadIdx.x; i <= K.nedges; i += blockDim.x) {
-        if (i < K.nedges) sh.thr[i] = K.thr[i];
-        sh.s1[i] = 0.0; sh.s2[i] = 0.0; sh.l2[i] = 0.0; sh.l4[i] = 0.0;
-        sh.cnt[i] = 0ull;
-    }
-}
-
-// np.digitize(k, edges) (right=False) evaluated on s = |k|^2/(2 pi)^2:
-// index = #{ j : thr[j] <= s }.   s is formed exactly like box.py:125-127,
-// ((Kx/Lx)^2 + (Ky/Ly)^2) + (Kz/Lz)^2 in float64 (per-axis squares precomputed by NumPy).
-__device__ __forceinline__ int pk_bin(const PkShared& sh, int nedges, double s) {
-    int lo = 0, hi = nedges;                 // first j with thr[j] > s
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sh.thr[mid] <= s) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// One mode per lane; lanes of a warp are aggregated by bin before touching smem.
-// w = multiplicity of the lane's mode (1 or 2), p = power, mu2 = (k_par/k)^2.
-__device__ __forceinline__ void pk_accumulate(PkShared& sh, int bin, float w, float p, float mu2, bool poles,
-                                              bool valid) {
-    const unsigned full = 0xffffffffu;
-    unsigned todo = __ballot_sync(full, valid);
-    const int lane = threadIdx.x & 31;
-    const unsigned wi = (unsigned)(w + 0.5f);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int lb = __shfl_sync(full, bin, leader);
-        const bool mine = valid && (bin == lb);
-        const unsigned grp = __ballot_sync(full, mine);
-        const unsigned cnt = __reduce_add_sync(full, mine ? wi : 0u);
-        const double pd = mine ? (double)p : 0.0;
-        const double wp = (double)w * pd;
-        double a1 = warp_sum(wp);
-        double a2 = warp_sum(wp * pd);
-        double b2 = 0.0, b4 = 0.0;
-        if (poles) {
-            const double m2 = (double)mu2;
-            b2 = warp_sum(wp * (1.5 * m2 - 0.5));
-            b4 = warp_sum(wp * ((35.0 * m2 * m2 - 30.0 * m2 + 3.0) * 0.125));
-        }
-        if (lane == leader) {
-            atomicAdd(&sh.cnt[lb], (unsigned long long)cnt);
-            atomicAdd(&sh.s1[lb], a1);
-            atomicAdd(&sh.s2[lb], a2);
-            if (poles) {
-                atomicAdd(&sh.l2[lb], b2);
-                atomicAdd(&sh.l4[lb], b4);
-            }
-        }
-        todo &= ~grp;
-    }
-}
-
-__device__ __forceinline__ void pk_shared_flush(PkShared& sh, const KSpace& K, const PkDev& out, bool poles) {
-    __syncthreads();
-    for (int i = threadIdx.x; i <= K.nedges; i += blockDim.x) {
-        if (sh.cnt[i]) {
-            atomicAdd(&out.count[i], sh.cnt[i]);
-            atomicAdd(&out.sum1[i], sh.s1[i]);
-            atomicAdd(&out.sum2[i], sh.s2[i]);
-            if (poles) {
-                atomicAdd(&out.l2[i], sh.l2[i]);
-                atomicAdd(&out.l4[i], sh.l4[i]);
-            }
-        }
-    }
 }
 
 }  // namespace fb

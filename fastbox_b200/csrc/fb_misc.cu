@@ -87,70 +87,109 @@ __global__ void __launch_bounds__(256) k_f32_to_f64(const float* __restrict__ sr
 
 // ---------------------------------------------------------------------------
 // Redshift-space remap, one CTA per line of sight (box.py:412-437).
-//   s = z - (v_z + v_nl)/H ; periodic wrap ; sort (s, delta) ; linear re-grid onto z
-//   (scipy griddata 1-D = argsort + interp1d(linear, fill_value)), coordinates in float64.
+//   s_l = z_l - (v_z + v_nl)_l / H, wrapped periodically into [z_0, z_{N-1});   out_l = linear
+//   re-grid of the scattered samples (s, delta) onto z  (scipy griddata 1-D = argsort +
+//   interp1d(linear, fill_value)): out(z) = y_lo + (y_hi-y_lo)/(x_hi-x_lo) (z-x_lo) with
+//   x_lo = largest sample < z, x_hi = smallest sample >= z; fill = (delta_0+delta_{N-1})/2 outside
+//   [min s, max s].
+// No sort is needed.  Every sample is dropped into the grid cell [z_c, z_{c+1}) that contains it,
+// keeping per cell the largest and the smallest sample (64-bit shared-memory atomic max / min on an
+// order-preserving key that carries the sample index in its low bits).  The bracket of output z_l is
+// then the max of the nearest non-empty cell below l and the min of the nearest non-empty cell at or
+// above l -- exactly the pair the sorted search returns -- found in O(1) expected steps.
+// Coordinates in float64 like the reference.
 // ---------------------------------------------------------------------------
+#define FB_RSD_IDX_BITS 12
 template <int N>
-__global__ void __launch_bounds__((N / 2) < 32 ? 32 : (N / 2)) k_rsd_remap(const float* __restrict__ delta,
-                                                                          const float* __restrict__ vel,
-                                                                          const float* __restrict__ vnl,
-                                                                          const double* __restrict__ zgrid,
-                                                                          double Hz, float* __restrict__ out) {
-    __shared__ double key[N];
-    __shared__ float val[N];
-    __shared__ double zz[N];
+__global__ void __launch_bounds__(256) k_rsd_remap(const float* __restrict__ delta, const float* __restrict__ vel,
+                                                    const float* __restrict__ vnl, const double* __restrict__ zgrid,
+                                                    double Hz, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char rsd_smem[];
+    double* u = reinterpret_cast<double*>(rsd_smem);                     // wrapped sample positions [N]
+    double* zz = u + N;                                                   // grid [N]
+    unsigned long long* cmax = reinterpret_cast<unsigned long long*>(zz + N);   // per cell: largest sample
+    unsigned long long* cmin = cmax + N;                                  // per cell: smallest sample
+    float* y = reinterpret_cast<float*>(cmin + N);                        // [N]
+    __shared__ double rmin[8], rmax[8];
+    __shared__ double s_min, s_max;
     const size_t line = (size_t)blockIdx.x * N;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const double zmin = zgrid[0], zmax = zgrid[N - 1];       // grid is increasing (linspace, box.py:79-88)
+    const double zmin = zgrid[0], zmax = zgrid[N - 1];       // increasing grid (linspace, box.py:79-88)
     const double length = zmax - zmin;
+    const double inv_dz = (double)(N - 1) / length, inv_len = 1.0 / length, inv_H = 1.0 / Hz;
     for (int l = tid; l < N; l += nt) {
-        const double zl = zgrid[l];
-        zz[l] = zl;
+        zz[l] = zgrid[l];
+        cmax[l] = 0ull;
+        cmin[l] = ~0ull;
+        y[l] = delta[line + l];
+    }
+    __syncthreads();
+    double lmin = 1e300, lmax = -1e300;
+    constexpr unsigned long long LOW = (1ull << FB_RSD_IDX_BITS) - 1ull;
+    for (int l = tid; l < N; l += nt) {
         double v = (double)vel[line + l];
         if (vnl) v += (double)vnl[line + l];
-        double s = zl - v / Hz;                                // box.py:422
-        double r = fmod(s - zmin, length);                     // Python float % : sign of divisor
-        if (r != 0.0 && r < 0.0) r += length;
-        key[l] = r + zmin;                                     // box.py:426
-        val[l] = delta[line + l];
+        const double s = zz[l] - v * inv_H;                    // box.py:422 (reciprocal: 1 ulp, no fp64 divide)
+        // (s - zmin) % length + zmin with Python's sign convention (box.py:425-426)
+        double r = s - zmin;
+        r -= floor(r * inv_len) * length;
+        if (r < 0.0) r += length;
+        if (r >= length) r -= length;
+        const double w = r + zmin;
+        u[l] = w;
+        lmin = fmin(lmin, w);
+        lmax = fmax(lmax, w);
+        // cell c with zz[c] <= w < zz[c+1] (exact w.r.t. the actual grid values)
+        int c = (int)(r * inv_dz);
+        c = max(0, min(c, N - 1));
+        while (c + 1 < N && w >= zz[c + 1]) ++c;
+        while (c > 0 && w < zz[c]) --c;
+        const unsigned long long key = (((unsigned long long)__double_as_longlong(r)) & ~LOW) | (unsigned long long)(l + 1);
+        atomicMax(&cmax[c], key);
+        atomicMin(&cmin[c], key);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((tid & 31) == 0) {
+        rmin[tid >> 5] = lmin;
+        rmax[tid >> 5] = lmax;
     }
     __syncthreads();
-    const float fill = 0.5f * (val[0] + val[N - 1]);           // box.py:429 (before sorting)
-    __syncthreads();
-    // bitonic sort, ascending in key
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < N / 2; i += nt) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const bool up = (lo & k) == 0;
-                const double a = key[lo], b = key[hi];
-                if ((a > b) == up) {
-                    key[lo] = b;
-                    key[hi] = a;
-                    const float t = val[lo];
-                    val[lo] = val[hi];
-                    val[hi] = t;
-                }
-            }
-            __syncthreads();
+    if (tid == 0) {
+        double b = 1e300, c = -1e300;
+        for (int i = 0; i < (nt + 31) / 32; ++i) {
+            b = fmin(b, rmin[i]);
+            c = fmax(c, rmax[i]);
         }
+        s_min = b;
+        s_max = c;
     }
-    const double x_first = key[0], x_last = key[N - 1];
+    __syncthreads();
+    const double xs_first = s_min, xs_last = s_max;
+    const float fill = 0.5f * (y[0] + y[N - 1]);               // box.py:429
     for (int l = tid; l < N; l += nt) {
         const double x = zz[l];
-        int lo = 0, hi = N;                                   // searchsorted(xs, x, 'left')
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (key[mid] < x) lo = mid + 1; else hi = mid;
+        double r;
+        if (x < xs_first || x > xs_last) {
+            r = (double)fill;                                  // outside the sampled range
+        } else {
+            int il = -1, ih = -1;
+            for (int c = l - 1; c >= 0; --c)                   // largest sample < x
+                if (cmax[c]) { il = (int)(cmax[c] & LOW) - 1; break; }
+            for (int c = l; c < N; ++c)                        // smallest sample >= x
+                if (cmin[c] != ~0ull) { ih = (int)(cmin[c] & LOW) - 1; break; }
+            if (ih < 0) ih = il;                               // cannot happen when x <= xs_last
+            if (il < 0) {
+                r = (double)y[ih];                             // x == smallest sample
+            } else {
+                // differences of nearby float64 positions are exact; the weight itself only needs float32
+                const double xl = u[il];
+                const float wgt = (float)(x - xl) / (float)(u[ih] - xl);
+                r = (double)fmaf(y[ih] - y[il], wgt, y[il]);
+            }
         }
-        int ih = lo < 1 ? 1 : (lo > N - 1 ? N - 1 : lo);
-        const int il = ih - 1;
-        const double xl = key[il], xh = key[ih];
-        const double yl = (double)val[il], yh = (double)val[ih];
-        const double slope = (yh - yl) / (xh - xl);
-        double r = slope * (x - xl) + yl;
-        if (x < x_first || x > x_last) r = (double)fill;
         out[line + l] = (float)r;
     }
 }
@@ -294,8 +333,13 @@ int fb_rsd_remap(fb_plan* p, const float* delta, const float* vel_z, const float
     FB_CUDA(cudaMemcpyAsync(p->aux, zgrid, (size_t)N * sizeof(double), cudaMemcpyDefault, p->stream));
     const unsigned lines = (unsigned)((size_t)N * N);
 #define FB_RSD(N_)                                                                                         \
-    k_rsd_remap<N_><<<lines, ((N_ / 2) < 32 ? 32 : (N_ / 2)), 0, p->stream>>>(                             \
-        (const float*)dd, (const float*)dv, (const float*)dn, (const double*)p->aux, Hz, (float*)dout)
+    {                                                                                                      \
+        auto kern = k_rsd_remap<N_>;                                                                       \
+        const size_t smem = (size_t)N_ * (8 + 8 + 8 + 8 + 4);                                              \
+        if (set_smem(kern, smem)) return -2;                                                               \
+        kern<<<lines, (N_ < 256 ? (N_ < 32 ? 32 : N_) : 256), smem, p->stream>>>(                          \
+            (const float*)dd, (const float*)dv, (const float*)dn, (const double*)p->aux, Hz, (float*)dout);  \
+    }
     FB_DISPATCH_N(N, FB_RSD);
 #undef FB_RSD
     FB_LAUNCH_CHECK();

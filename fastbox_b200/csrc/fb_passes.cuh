@@ -13,6 +13,7 @@
 namespace fb {
 
 enum { SRC_NOISE = 0, SRC_PHILOX = 1, SRC_SPEC = 2, SRC_CUBE = 3 };
+#define FB_F_FULLCUBE_INTERNAL 1024   // P(k) of a full (non-Hermitian) cube: every plane has weight 1
 
 #ifndef FB_ROWS_MINB
 #define FB_ROWS_MINB 3      // CTAs per SM the row kernels are compiled for (register cap 65536/(256*MINB))
@@ -254,9 +255,10 @@ __device__ __forceinline__ void run_amp(const KSpace& K, int flags, int kind, in
 // (very low |k|, or multipoles requested) each lane walks its run mode by mode.
 template <int N, int P, bool MONOTONE>
 __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, const PkDev& out, int a, int b, int c0,
-                                       const float2 (&h)[P], const float2* x, bool poles, bool rvalid) {
+                                       const float2 (&h)[P], const float2* x, bool poles, bool rvalid,
+                                       bool full_cube = false) {
     const unsigned full = 0xffffffffu;
-    const float wmult = (a == 0 || a == N / 2) ? 1.f : 2.f;
+    const float wmult = (full_cube || a == 0 || a == N / 2) ? 1.f : 2.f;
     const unsigned wi = (unsigned)(wmult + 0.5f);
     const double sab = __dadd_rn(K.ax[a], K.ay[b]);
     const float invb = (float)K.inv_boxfactor;
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
 // rows, forward: c <- z on work[a][b][:], then optional store + P(k) binning
 // (auto |S|^2 or cross Re S conj(X)).   grid = ceil(na*N / RB)
 // ---------------------------------------------------------------------------
-template <int N>
+template <int N, bool DOFFT>
 __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_fwd(const RowsArgs A) {
     using G = RowGeom<N>;
     using C = FftCfg<N>;
@@ -493,7 +495,8 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_fwd(
     PkTables tb;
     if (do_pk) tb = pk_stage_tables<N>(A.K, reinterpret_cast<double*>(smem_raw + G::FFT_SMEM));
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
-    fft_regs<N, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, A.tw);
+    if constexpr (DOFFT) fft_regs<N, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, A.tw);   // else: binning only
+    const bool full_cube = (A.flags & FB_F_FULLCUBE_INTERNAL) != 0;
     if (T == 1 && do_pk) __syncthreads();
     if constexpr (T > 1) {
         __syncthreads();
@@ -520,9 +523,9 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_fwd(
         if (A.cross) {
             float2 x[P];
             load_run<P>(A.cross + row_local + c0, x);
-            run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, x, poles, rvalid);
+            run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, x, poles, rvalid, full_cube);
         } else {
-            run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, nullptr, poles, rvalid);
+            run_pk<N, P, (T > 1)>(A.K, tb, A.pk, a, b, c0, hr, nullptr, poles, rvalid, full_cube);
         }
     }
 }
