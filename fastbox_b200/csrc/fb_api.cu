@@ -160,6 +160,9 @@ fb::KSpace fb_plan::kspace() const {
     K.sqrtp_n = (int)sqrtp_n;
     K.log2s0 = (float)log2s0;
     K.inv_dlog2s = dlog2s > 0 ? (float)(1.0 / dlog2s) : 0.f;
+    K.bt_shift = 23 - (int)dlog2s;                       // mode 3: dlog2s carries M, log2s0 carries the base index
+    K.bt_base = (int)log2s0;
+    K.bt_scale = 1.0f / (float)(1u << (K.bt_shift > 0 && K.bt_shift < 24 ? K.bt_shift : 1));
     K.tperp = tperp;
     K.tpar = tpar;
     K.tdense = tdense;
@@ -346,11 +349,12 @@ static int upload_table(float** slot, size_t* cap, const float* host, size_t n) 
 
 int fb_set_sqrt_pk(fb_plan* p, const float* table, long n, int mode, double log2s0, double dlog2s) {
     FB_CUDA(cudaStreamSynchronize(p->stream));
-    FB_CHECK(mode == 1 || mode == 2, "fb_set_sqrt_pk: mode must be 1 (integer LUT) or 2 (log2 table)");
+    FB_CHECK(mode >= 1 && mode <= 3, "fb_set_sqrt_pk: mode must be 1 (integer LUT), 2 (log2 table) or 3 (float-bit table)");
+    if (mode == 3) FB_CHECK(dlog2s >= 4 && dlog2s <= 16 && n >= 2, "fb_set_sqrt_pk: mode 3 needs 4 <= M <= 16 mantissa bits");
     if (mode == 1) {
         const long need = 3L * (p->N / 2) * (p->N / 2) + 1;
         FB_CHECK(n >= need, "fb_set_sqrt_pk: integer LUT needs %ld entries, got %ld", need, n);
-    } else {
+    } else if (mode == 2) {
         FB_CHECK(n >= 2 && dlog2s > 0, "fb_set_sqrt_pk: log table needs n>=2 and dlog2s>0");
     }
     if (upload_table(&p->sqrtp, &p->tab_cap[0], table, (size_t)n)) return -2;

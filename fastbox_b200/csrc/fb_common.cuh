@@ -57,6 +57,8 @@ struct KSpace {
     int sqrtp_mode;         // 0 none, 1 integer |m|^2 LUT, 2 log2(s) table
     int sqrtp_n;
     float log2s0, inv_dlog2s;
+    int bt_shift, bt_base;  // mode 3: index = (float_bits(s) >> bt_shift) - bt_base
+    float bt_scale;         //         fraction = low bits * bt_scale
     // filter
     const float* tperp;     // [(N/2+1)*N]
     const float* tpar;      // [N]

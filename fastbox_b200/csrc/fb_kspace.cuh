@@ -22,6 +22,19 @@ __device__ __forceinline__ float sqrtp_logtable(const KSpace& K, float s) {
     return fmaf(0.5f * f, fmaf(f, fmaf(f, c3, c2), p2 - p0), p1);
 }
 
+// sqrt(P) from a table indexed by the leading bits of float(s) (exponent + M mantissa bits) with
+// linear interpolation inside the segment: geometric node spacing without a log2, two adjacent
+// loads (L1 resident), ~10 instructions.  Validated on the host like the log2 table.
+__device__ __forceinline__ float sqrtp_bittable(const KSpace& K, float s) {
+    if (!(s > 0.f)) return 0.f;                          // nan_to_num(P(0)) = 0, box.py:167
+    const unsigned key = __float_as_uint(s);
+    int i = (int)(key >> K.bt_shift) - K.bt_base;
+    i = max(0, min(i, K.sqrtp_n - 2));
+    const float frac = (float)(key & ((1u << K.bt_shift) - 1u)) * K.bt_scale;
+    const float t0 = __ldg(&K.sqrtp[i]), t1 = __ldg(&K.sqrtp[i + 1]);
+    return fmaf(frac, t1 - t0, t0);
+}
+
 // real multiplier for mode (a,b,c) (global indices); `cf` = index used for the k_par /
 // dense filter lookup (c itself, or (N-c)%N when the factor at -k is wanted).
 __device__ __forceinline__ float k_amp(const KSpace& K, int flags, int kind, int a, int b, int c, int cf) {
@@ -32,10 +45,11 @@ __device__ __forceinline__ float k_amp(const KSpace& K, int flags, int kind, int
     if ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 1) {
         amp = __ldg(&K.sqrtp[ma * ma + mb * mb + mc * mc]);
     }
-    if (kind != FB_KIND_PLAIN || ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 2)) {
+    if (kind != FB_KIND_PLAIN || ((flags & FB_F_SQRTPK) && K.sqrtp_mode >= 2)) {
         s = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2 + (float)(mc * mc) * K.inv_lz2;
     }
     if ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 2) amp = sqrtp_logtable(K, s);
+    if ((flags & FB_F_SQRTPK) && K.sqrtp_mode == 3) amp = sqrtp_bittable(K, s);
     if (flags & FB_F_FILTER) {
         if (K.tdense)
             amp *= __ldg(&K.tdense[((size_t)a * N + b) * N + cf]);

@@ -208,11 +208,12 @@ __device__ __forceinline__ void run_amp(const KSpace& K, int flags, int kind, in
             }
         } else {
             const float sab = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2;
+            const bool bits = K.sqrtp_mode == 3;
 #pragma unroll
             for (int e = 0; e < P; ++e) {
                 const int mc = half < 0 ? mode_number(c0 + e, N) : c0 + e + moff;
-                const float val = sqrtp_logtable(K, sab + (float)(mc * mc) * K.inv_lz2);
-                amp[e] *= val;
+                const float sv = sab + (float)(mc * mc) * K.inv_lz2;
+                amp[e] *= bits ? sqrtp_bittable(K, sv) : sqrtp_logtable(K, sv);
             }
         }
     }

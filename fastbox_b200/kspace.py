@@ -120,13 +120,44 @@ def eval_log_table(tab, l0, dl, s):
     return out
 
 
+def sqrt_pk_bit_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, M=9):
+    """
+    Table indexed by the leading bits (exponent + M mantissa bits) of float32(s): geometric node
+    spacing, linear interpolation inside a segment (fb_kspace.cuh:sqrtp_bittable).
+    Returns (table float32, base index, M).
+    """
+    smin = min(1.0 / Lx ** 2, 1.0 / Ly ** 2, 1.0 / Lz ** 2)
+    smax = (N / 2.0) ** 2 * (1.0 / Lx ** 2 + 1.0 / Ly ** 2 + 1.0 / Lz ** 2)
+    sh = np.uint32(23 - M)
+    k0 = int(np.float32(smin * 0.999).view(np.uint32) >> sh) - 1
+    k1 = int(np.float32(smax * 1.001).view(np.uint32) >> sh) + 2
+    nodes = (np.arange(k0, k1 + 1, dtype=np.uint32) << sh).view(np.float32).astype(np.float64)
+    pk = np.nan_to_num(np.asarray(pk_of_k(TWO_PI * np.sqrt(nodes)), dtype=np.float64))
+    return np.sqrt(pk * boxfactor).astype(np.float32), k0, M
+
+
+def eval_bit_table(tab, base, M, s):
+    """Host emulation of fb_kspace.cuh:sqrtp_bittable (s is rounded to float32 like on the device)."""
+    s32 = np.asarray(s, dtype=np.float32)
+    out = np.zeros(s32.shape)
+    ok = s32 > 0
+    key = s32[ok].view(np.uint32)
+    i = np.clip((key >> np.uint32(23 - M)).astype(np.int64) - base, 0, tab.size - 2)
+    frac = (key & np.uint32((1 << (23 - M)) - 1)).astype(np.float64) * 2.0 ** -(23 - M)
+    t = tab.astype(np.float64)
+    out[ok] = t[i] + frac * (t[i + 1] - t[i])
+    return out
+
+
 def choose_sqrt_pk_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, rtol=2e-6, exact_below=512):
     """
     Pick the sqrt(P) representation for the device.
       mode 1: exact integer LUT (cubic boxes).  Its gathers miss L1, so it is used for small grids
               and whenever the interpolated table cannot be validated;
-      mode 2: log2(s) table + cubic interpolation, validated here against the exact values at
-              every distinct |k| of a cubic box (or 2^20 random modes of a cuboid).
+      mode 3: table indexed by the leading bits of float32(s) + linear interpolation (preferred);
+      mode 2: log2(s) table + cubic interpolation;
+              both validated here against the exact values at every distinct |k| of a cubic box
+              (or 2^20 random modes of a cuboid).
     Returns (mode, table, log2s0, dlog2s).
     """
     cubic = (Lx == Ly == Lz)
@@ -142,10 +173,14 @@ def choose_sqrt_pk_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, rtol=2e-6, exact_bel
         s = s[s > 0]
     exact = np.sqrt(np.nan_to_num(np.asarray(pk_of_k(TWO_PI * np.sqrt(s)), dtype=np.float64)) * boxfactor)
     scale = np.max(np.abs(exact))
+    floor = np.maximum(np.abs(exact), 1e-6 * scale)
+    for M in (9, 10, 11):                                # float-bit table: cheapest on the device
+        tab, base, M = sqrt_pk_bit_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, M)
+        if np.max(np.abs(eval_bit_table(tab, base, M, s) - exact) / floor) < rtol:
+            return 3, tab, float(base), float(M)
     for npts in (4096, 16384, 65536):
         tab, l0, dl = sqrt_pk_log_table(pk_of_k, N, Lx, Ly, Lz, boxfactor, npts)
-        err = np.max(np.abs(eval_log_table(tab, l0, dl, s) - exact) / np.maximum(np.abs(exact), 1e-6 * scale))
-        if err < rtol:
+        if np.max(np.abs(eval_log_table(tab, l0, dl, s) - exact) / floor) < rtol:
             return 2, tab, l0, dl
     if cubic:
         return 1, sqrt_pk_int_lut(pk_of_k, N, Lx, boxfactor), 0.0, 0.0

@@ -96,7 +96,9 @@ int fb_device_info(int device, char* name, int name_len, int* sm_count, size_t* 
 /* ---- tables ---------------------------------------------------------------- */
 /* sqrt(P(k) * boxfactor), box.py:161-171.  mode 1: cubic box, exact LUT indexed
  * by the integer i^2+j^2+l^2 (n entries);  mode 2: table uniform in log2(s),
- * s = (i/Lx)^2+(j/Ly)^2+(l/Lz)^2, with origin log2s0 and spacing dlog2s.       */
+ * s = (i/Lx)^2+(j/Ly)^2+(l/Lz)^2, with origin log2s0 and spacing dlog2s (cubic interpolation);
+ * mode 3: table indexed by the leading bits of float32(s): entry i is the value at the float whose
+ * bit pattern is (i + base) << (23 - M); pass base in `log2s0` and M (mantissa bits) in `dlog2s`. */
 int fb_set_sqrt_pk(fb_plan* plan, const float* table, long n, int mode, double log2s0, double dlog2s);
 /* transfer function T(k_perp, k_par), box.py:374-378.  Separable form
  * tperp[(N/2+1)*N] (index a*N+b) times tpar[N]; or dense [(N/2+1)*N*N].

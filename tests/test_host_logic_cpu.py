@@ -63,8 +63,11 @@ def test_sqrt_pk_tables():
     assert np.all(interp[~ok] == 0.0)
     # the chooser validates the interpolated table and keeps small cubic grids exact
     assert ks.choose_sqrt_pk_table(pkf, 32, 500., 500., 500., bf)[0] == 1
-    mode, t2, a0, d0 = ks.choose_sqrt_pk_table(pkf, 32, 500., 500., 500., bf, exact_below=0)
-    assert mode == 2 and t2.size == 4096
+    mode, t2, base, M = ks.choose_sqrt_pk_table(pkf, 32, 500., 500., 500., bf, exact_below=0)
+    assert mode == 3 and M == 9.0                          # float-bit table, 9 mantissa bits
+    n2 = np.arange(1, 3 * 16 ** 2 + 1, dtype=np.float64)
+    exact = np.sqrt(pkf(2 * np.pi * np.sqrt(n2) / 500.) * bf)
+    assert np.allclose(ks.eval_bit_table(t2, int(base), int(M), n2 / 500. ** 2), exact, rtol=2e-6)
     spiky = lambda k: pkf(k) * (1.0 + 0.9 * np.sin(k * 2.0e4))          # cannot be interpolated: falls back
     assert ks.choose_sqrt_pk_table(spiky, 32, 500., 500., 500., bf, exact_below=0)[0] == 1
 
