@@ -233,14 +233,15 @@ class Plan(object):
 
     # -- pipelines ----------------------------------------------------------
     def realise(self, re=None, im=None, seed=0, flags=F_SQRTPK, scale=1.0, field_out=None, spec_out=None,
-                want_pk=False, poles=False):
+                want_pk=False, poles=False, want_sums=True):
         """fb_realise.  Buffers may be numpy (host), DeviceBuffer or torch tensors."""
         st, res = (self._pk_struct(poles) if want_pk else (None, None))
         if want_pk and poles:
             flags |= F_POLES
         sums = (C.c_double * 2)()
         check(self.lib.fb_realise(self.h, _ptr(re), _ptr(im), int(seed), int(flags), float(scale), _ptr(field_out),
-                                  _ptr(spec_out), C.byref(st) if st is not None else None, sums))
+                                  _ptr(spec_out), C.byref(st) if st is not None else None,
+                                  sums if want_sums else None))
         return res, (sums[0], sums[1])
 
     def spectrum_to_field(self, spec, field_out, flags=0, kind=KIND_PLAIN, scale=1.0):

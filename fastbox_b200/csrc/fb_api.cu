@@ -465,7 +465,7 @@ int fb_realise(fb_plan* p, const float* re, const float* im, uint64_t seed, int 
     mark(p, 0);
     if (re ? launch_rows_inv_noise(p, ra) : launch_rows_inv_philox(p, ra)) return -3;
     mark(p, 1);
-    if (inverse_tail(p, flags, scale, (float*)dfield, p->scal)) return -3;
+    if (inverse_tail(p, flags, scale, (float*)dfield, sum_out ? p->scal : nullptr)) return -3;   // sums only on request
     if (stage_out_end(p, 2, field_out, n3 * sizeof(float))) return -2;
     if (stage_out_end(p, 3, spec_out, nh * sizeof(float2))) return -2;
     if (pk && pk_fetch(p, pk)) return -2;
@@ -501,7 +501,7 @@ int fb_spectrum_to_field(fb_plan* p, const void* spec_half, int flags, int kind,
     mark(p, 0);
     if (launch_rows_inv_spec(p, ra)) return -3;
     mark(p, 1);
-    if (inverse_tail(p, flags, scale, (float*)dfield, p->scal)) return -3;
+    if (inverse_tail(p, flags, scale, (float*)dfield, sum_out ? p->scal : nullptr)) return -3;
     if (stage_out_end(p, 2, field_out, n3 * sizeof(float))) return -2;
     if (scal_fetch(p, sum_out, 2)) return -2;
     return 0;

@@ -100,97 +100,128 @@ __global__ void __launch_bounds__(256) k_f32_to_f64(const float* __restrict__ sr
 // Coordinates in float64 like the reference.
 // ---------------------------------------------------------------------------
 #define FB_RSD_IDX_BITS 12
+#define FB_RSD_LPC 8            // lines of sight per CTA (software pipelined)
 template <int N>
-__global__ void __launch_bounds__(256) k_rsd_remap(const float* __restrict__ delta, const float* __restrict__ vel,
-                                                    const float* __restrict__ vnl, const double* __restrict__ zgrid,
-                                                    double Hz, float* __restrict__ out) {
+struct RsdGeom {
+    static constexpr int NT = N >= 256 ? 256 : (N < 32 ? 32 : N);
+    static constexpr int E = (N + NT - 1) / NT;                      // elements per thread
+    static constexpr size_t SMEM = (size_t)N * (8 + 2 * (8 + 4 + 4 + 4));   // zz + 2 x (u, cmax, cmin, y)
+};
+
+template <int N>
+__global__ void __launch_bounds__(RsdGeom<N>::NT) k_rsd_remap(const float* __restrict__ delta,
+                                                              const float* __restrict__ vel,
+                                                              const float* __restrict__ vnl,
+                                                              const double* __restrict__ zgrid, double Hz,
+                                                              float* __restrict__ out, long nlines) {
+    constexpr int NT = RsdGeom<N>::NT, E = RsdGeom<N>::E;
     extern __shared__ __align__(16) unsigned char rsd_smem[];
-    double* u = reinterpret_cast<double*>(rsd_smem);                     // wrapped sample positions [N]
-    double* zz = u + N;                                                   // grid [N]
-    unsigned long long* cmax = reinterpret_cast<unsigned long long*>(zz + N);   // per cell: largest sample
-    unsigned long long* cmin = cmax + N;                                  // per cell: smallest sample
-    float* y = reinterpret_cast<float*>(cmin + N);                        // [N]
-    __shared__ double rmin[8], rmax[8];
-    __shared__ double s_min, s_max;
-    const size_t line = (size_t)blockIdx.x * N;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    double* zz = reinterpret_cast<double*>(rsd_smem);                 // grid [N]
+    double* u2 = zz + N;                                              // wrapped sample positions [2][N]
+    unsigned* cmax2 = reinterpret_cast<unsigned*>(u2 + 2 * N);        // per cell: largest sample (32-bit key)
+    unsigned* cmin2 = cmax2 + 2 * N;                                  // per cell: smallest sample
+    float* y2 = reinterpret_cast<float*>(cmin2 + 2 * N);              // [2][N]
+    const int tid = threadIdx.x;
     const double zmin = zgrid[0], zmax = zgrid[N - 1];       // increasing grid (linspace, box.py:79-88)
     const double length = zmax - zmin;
     const double inv_dz = (double)(N - 1) / length, inv_len = 1.0 / length, inv_H = 1.0 / Hz;
-    for (int l = tid; l < N; l += nt) {
+    // key = position inside the cell (20 bits) | sample index + 1 (12 bits): native 32-bit smem atomics
+    constexpr unsigned LOW = (1u << FB_RSD_IDX_BITS) - 1u;
+    for (int l = tid; l < N; l += NT) {
         zz[l] = zgrid[l];
-        cmax[l] = 0ull;
-        cmin[l] = ~0ull;
-        y[l] = delta[line + l];
+        cmax2[l] = 0u;
+        cmin2[l] = ~0u;
     }
-    __syncthreads();
-    double lmin = 1e300, lmax = -1e300;
-    constexpr unsigned long long LOW = (1ull << FB_RSD_IDX_BITS) - 1ull;
-    for (int l = tid; l < N; l += nt) {
-        double v = (double)vel[line + l];
-        if (vnl) v += (double)vnl[line + l];
-        const double s = zz[l] - v * inv_H;                    // box.py:422 (reciprocal: 1 ulp, no fp64 divide)
-        // (s - zmin) % length + zmin with Python's sign convention (box.py:425-426)
-        double r = s - zmin;
-        r -= floor(r * inv_len) * length;
-        if (r < 0.0) r += length;
-        if (r >= length) r -= length;
-        const double w = r + zmin;
-        u[l] = w;
-        lmin = fmin(lmin, w);
-        lmax = fmax(lmax, w);
-        // cell c with zz[c] <= w < zz[c+1] (exact w.r.t. the actual grid values)
-        int c = (int)(r * inv_dz);
-        c = max(0, min(c, N - 1));
-        while (c + 1 < N && w >= zz[c + 1]) ++c;
-        while (c > 0 && w < zz[c]) --c;
-        const unsigned long long key = (((unsigned long long)__double_as_longlong(r)) & ~LOW) | (unsigned long long)(l + 1);
-        atomicMax(&cmax[c], key);
-        atomicMin(&cmin[c], key);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-        lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-    }
-    if ((tid & 31) == 0) {
-        rmin[tid >> 5] = lmin;
-        rmax[tid >> 5] = lmax;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double b = 1e300, c = -1e300;
-        for (int i = 0; i < (nt + 31) / 32; ++i) {
-            b = fmin(b, rmin[i]);
-            c = fmax(c, rmax[i]);
-        }
-        s_min = b;
-        s_max = c;
-    }
-    __syncthreads();
-    const double xs_first = s_min, xs_last = s_max;
-    const float fill = 0.5f * (y[0] + y[N - 1]);               // box.py:429
-    for (int l = tid; l < N; l += nt) {
-        const double x = zz[l];
-        double r;
-        if (x < xs_first || x > xs_last) {
-            r = (double)fill;                                  // outside the sampled range
-        } else {
-            int il = -1, ih = -1;
-            for (int c = l - 1; c >= 0; --c)                   // largest sample < x
-                if (cmax[c]) { il = (int)(cmax[c] & LOW) - 1; break; }
-            for (int c = l; c < N; ++c)                        // smallest sample >= x
-                if (cmin[c] != ~0ull) { ih = (int)(cmin[c] & LOW) - 1; break; }
-            if (ih < 0) ih = il;                               // cannot happen when x <= xs_last
-            if (il < 0) {
-                r = (double)y[ih];                             // x == smallest sample
-            } else {
-                // differences of nearby float64 positions are exact; the weight itself only needs float32
-                const double xl = u[il];
-                const float wgt = (float)(x - xl) / (float)(u[ih] - xl);
-                r = (double)fmaf(y[ih] - y[il], wgt, y[il]);
+    const long line0 = (long)blockIdx.x * FB_RSD_LPC;
+    const long line1 = line0 + FB_RSD_LPC < nlines ? line0 + FB_RSD_LPC : nlines;
+    float dcur[E], vcur[E];
+    auto fetch = [&](long ln, float (&d)[E], float (&v)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid + e * NT;
+            if (l < N) {
+                d[e] = delta[(size_t)ln * N + l];
+                v[e] = vel[(size_t)ln * N + l] + (vnl ? vnl[(size_t)ln * N + l] : 0.f);
             }
         }
-        out[line + l] = (float)r;
+    };
+    if (line0 < line1) fetch(line0, dcur, vcur);
+    __syncthreads();
+    int cur = 0;
+    for (long ln = line0; ln < line1; ++ln, cur ^= 1) {
+        double* u = u2 + cur * N;
+        float* y = y2 + cur * N;
+        unsigned *cmax = cmax2 + cur * N, *cmin = cmin2 + cur * N;
+        float dnext[E], vnext[E];
+        if (ln + 1 < line1) fetch(ln + 1, dnext, vnext);            // in flight while this line is processed
+        // ---- phase 1: wrapped positions, per-cell extremes; reset the other buffer's cells
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid + e * NT;
+            if (l < N) {
+                const double s = zz[l] - (double)vcur[e] * inv_H;     // box.py:422 (float add of v_nl, reciprocal of H)
+                // (s - zmin) % length + zmin with Python's sign convention (box.py:425-426)
+                double r = s - zmin;
+                r -= floor(r * inv_len) * length;
+                if (r < 0.0) r += length;
+                if (r >= length) r -= length;
+                const double w = r + zmin;
+                u[l] = w;
+                y[l] = dcur[e];
+                // cell c with zz[c] <= w < zz[c+1] (exact w.r.t. the actual grid values)
+                int c = (int)(r * inv_dz);
+                c = max(0, min(c, N - 1));
+                while (c + 1 < N && w >= zz[c + 1]) ++c;
+                while (c > 0 && w < zz[c]) --c;
+                const float fpos = (float)((w - zz[c]) * inv_dz);          // in [0, 1)
+                const unsigned qpos = min((unsigned)(fmaxf(fpos, 0.f) * 1048576.f), 1048575u);
+                const unsigned key = (qpos << FB_RSD_IDX_BITS) | (unsigned)(l + 1);
+                atomicMax(&cmax[c], key);
+                atomicMin(&cmin[c], key);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: smallest / largest sample, then the bracket of every grid point
+        int cf = 0, cl = N - 1;
+        while (cf < N - 1 && cmin[cf] == ~0u) ++cf;
+        while (cl > 0 && cmax[cl] == 0u) --cl;
+        const double xs_first = u[(int)(cmin[cf] & LOW) - 1], xs_last = u[(int)(cmax[cl] & LOW) - 1];
+        const float fill = 0.5f * (y[0] + y[N - 1]);           // box.py:429
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int l = tid + e * NT;
+            if (l < N) {
+                const double x = zz[l];
+                float r;
+                if (x < xs_first || x > xs_last) {
+                    r = fill;                                  // outside the sampled range
+                } else {
+                    int il = -1, ih = -1;
+                    for (int c = l - 1; c >= 0; --c)           // largest sample < x
+                        if (cmax[c]) { il = (int)(cmax[c] & LOW) - 1; break; }
+                    for (int c = l; c < N; ++c)                // smallest sample >= x
+                        if (cmin[c] != ~0u) { ih = (int)(cmin[c] & LOW) - 1; break; }
+                    if (ih < 0) ih = il;                       // cannot happen when x <= xs_last
+                    if (il < 0) {
+                        r = y[ih];                             // x == smallest sample
+                    } else {
+                        // differences of nearby float64 positions are exact; the weight only needs float32
+                        const double xl = u[il];
+                        const float wgt = (float)(x - xl) / (float)(u[ih] - xl);
+                        r = fmaf(y[ih] - y[il], wgt, y[il]);
+                    }
+                }
+                out[(size_t)ln * N + l] = r;
+                cmax2[(cur ^ 1) * N + l] = 0u;                 // cells of the next line (idle during this one)
+                cmin2[(cur ^ 1) * N + l] = ~0u;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            dcur[e] = dnext[e];
+            vcur[e] = vnext[e];
+        }
+        __syncthreads();                                       // resets visible; this line's readers are done
     }
 }
 
@@ -331,14 +362,15 @@ int fb_rsd_remap(fb_plan* p, const float* delta, const float* vel_z, const float
     if (stage_out_begin(p, 2, out, n3 * sizeof(float), &dout)) return -2;
     if (ensure_aux(p, (size_t)N * sizeof(double))) return -2;
     FB_CUDA(cudaMemcpyAsync(p->aux, zgrid, (size_t)N * sizeof(double), cudaMemcpyDefault, p->stream));
-    const unsigned lines = (unsigned)((size_t)N * N);
+    const long nlines = (long)N * N;
+    const unsigned ctas = (unsigned)((nlines + FB_RSD_LPC - 1) / FB_RSD_LPC);
 #define FB_RSD(N_)                                                                                         \
     {                                                                                                      \
         auto kern = k_rsd_remap<N_>;                                                                       \
-        const size_t smem = (size_t)N_ * (8 + 8 + 8 + 8 + 4);                                              \
-        if (set_smem(kern, smem)) return -2;                                                               \
-        kern<<<lines, (N_ < 256 ? (N_ < 32 ? 32 : N_) : 256), smem, p->stream>>>(                          \
-            (const float*)dd, (const float*)dv, (const float*)dn, (const double*)p->aux, Hz, (float*)dout);  \
+        if (set_smem(kern, RsdGeom<N_>::SMEM)) return -2;                                                  \
+        kern<<<ctas, RsdGeom<N_>::NT, RsdGeom<N_>::SMEM, p->stream>>>(                                     \
+            (const float*)dd, (const float*)dv, (const float*)dn, (const double*)p->aux, Hz, (float*)dout, \
+            nlines);                                                                                       \
     }
     FB_DISPATCH_N(N, FB_RSD);
 #undef FB_RSD

@@ -711,17 +711,25 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     const size_t sstride = (size_t)(2 * T) * A.ncols;
     const bool do_exp = (A.flags & FB_F_EXP) != 0;
     float acc = 0.f, acc2 = 0.f;
+    if (A.sums || do_exp) {
 #pragma unroll
-    for (int q = 0; q < P; ++q, dst += sstride) {
-        float r0 = v[q].x * A.scale, r1 = v[q].y * A.scale;
-        if (do_exp) {
-            r0 = expf(r0);
-            r1 = expf(r1);
+        for (int q = 0; q < P; ++q, dst += sstride) {
+            float r0 = v[q].x * A.scale, r1 = v[q].y * A.scale;
+            if (do_exp) {
+                r0 = expf(r0);
+                r1 = expf(r1);
+            }
+            acc += r0 + r1;
+            acc2 = fmaf(r0, r0, fmaf(r1, r1, acc2));
+            dst[0] = r0;
+            dst[A.ncols] = r1;
         }
-        acc += r0 + r1;
-        acc2 = fmaf(r0, r0, fmaf(r1, r1, acc2));
-        dst[0] = r0;
-        dst[A.ncols] = r1;
+    } else {                                           // plain field: scale and store
+#pragma unroll
+        for (int q = 0; q < P; ++q, dst += sstride) {
+            dst[0] = v[q].x * A.scale;
+            dst[A.ncols] = v[q].y * A.scale;
+        }
     }
     if (A.sums) {
         double s1 = warp_sum((double)acc), s2 = warp_sum((double)acc2);
