@@ -126,6 +126,15 @@ class CudaEngine(object):
         return self.plan.fft_pass_x_c2r(self.recv, self.field, self.ny * N, flags=flags,
                                         scale=scale / float(N) ** 3)
 
+    def x_from_real(self):
+        """Forward x pass on the local y slab: ``self.field`` -> ``self.recv`` ([kx][y'][z])."""
+        self.plan.fft_pass_x_r2c(self.field, self.recv, self.ny * self.N)
+
+    def forward_kspace(self, want_pk=True, spec_out=None, poles=False):
+        """y columns + z rows on the local kx planes of the received spectrum (``self.send`` buffer)."""
+        return self.plan.forward_local_kspace(self.send, self.work, self.ny, spec_out=spec_out, want_pk=want_pk,
+                                              poles=poles)
+
     def sync(self):
         self.plan.sync()
 
@@ -210,6 +219,29 @@ class DistributedRealiser(object):
         arr = t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t)
         n = arr.size // 3
         return dict(count=np.rint(arr[:n]).astype(np.uint64), sum1=arr[n:2 * n], sum2=arr[2 * n:])
+
+    def exchange_back(self):
+        """Real-side slabs -> spectrum-side planes (the reverse all-to-all, used by the forward transform)."""
+        e = self.e
+        if e.world == 1:
+            e.send.reshape(-1).copy_(e.recv.reshape(-1))
+            return
+        self.dist.all_to_all_single(e.send.reshape(-1), e.recv.reshape(-1),
+                                    output_split_sizes=self.in_splits, input_split_sizes=self.out_splits,
+                                    group=self.group)
+
+    def power_spectrum(self):
+        """
+        Binned P(k) moments of the sharded real field in ``engine.field`` (box.py:736-764):
+        local x pass -> all-to-all -> local y and z passes with the histogram epilogue -> all-reduce.
+        """
+        e = self.e
+        e.x_from_real()
+        e.sync()
+        self.exchange_back()
+        e.sync_exchange()
+        res = e.forward_kspace(want_pk=True)
+        return self._reduce_moments(res)
 
     def realise(self, seed, flags, want_pk=False, scale=1.0):
         """

@@ -42,6 +42,12 @@ def test_world1_pipeline_equals_fused_call(gpu, N):
     assert rel_l2(got, ref.astype(np.float64)) < 1e-6
     assert np.array_equal(pk["count"], res_ref["count"])
     assert np.allclose(pk["sum1"], res_ref["sum1"], rtol=1e-12)
+    # forward direction through the same building blocks: P(k) of the realised (filtered) field
+    pkf = dr.power_spectrum()
+    assert np.array_equal(pkf["count"], res_ref["count"])
+    m = res_ref["count"] > 0
+    floor = 1e-12 * np.abs(res_ref["sum1"]).max()
+    assert np.all(np.abs(pkf["sum1"][m] - res_ref["sum1"][m]) <= 2e-5 * np.abs(res_ref["sum1"][m]) + floor)
 
 
 def test_two_slabs_emulated_on_one_gpu(gpu):

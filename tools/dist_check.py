@@ -57,7 +57,15 @@ def main():
             print("N=%d world=%d field rel-L2 %.2e, counts equal %s, sum1 rel err %.1e" % (N, world, err, same_counts,
                                                                                           pk_err), flush=True)
             ok = ok and err < 1e-6 and same_counts and pk_err < 1e-10
+            fwd_ref = plan.field_to_spectrum(ref, want_pk=True)
             plan.close()
+        # forward direction: P(k) of the sharded field through the reverse all-to-all
+        pk_f = dr.power_spectrum()
+        if rank == 0:
+            same = np.array_equal(pk_f["count"], fwd_ref["count"])
+            e1 = np.nanmax(np.abs(pk_f["sum1"] - fwd_ref["sum1"]) / np.maximum(np.abs(fwd_ref["sum1"]), 1e-300))
+            print("      forward P(k): counts equal %s, sum1 rel err %.1e" % (same, e1), flush=True)
+            ok = ok and same and e1 < 1e-10
         dist.barrier()
     if rank == 0:
         print("DIST CHECK", "OK" if ok else "FAILED", flush=True)
