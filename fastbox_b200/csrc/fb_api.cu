@@ -102,29 +102,40 @@ int pk_clear(fb_plan* p) {
     return 0;
 }
 
+// the device histogram is replicated FB_PK_COPIES times (CTAs spread their reductions over the
+// copies so that no single L2 address serialises them); fold the copies on the device, then one
+// small pinned D2H copy
+__global__ void k_pk_fold(const unsigned long long* __restrict__ cnt, const double* __restrict__ sums,
+                          unsigned long long* __restrict__ cnt_out, double* __restrict__ sums_out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long c = 0;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < FB_PK_COPIES; ++k) {
+        c += cnt[(size_t)k * (FB_MAX_EDGES + 1) + i];
+        for (int j = 0; j < 4; ++j)
+            s[j] += sums[((size_t)j * FB_PK_COPIES + k) * (FB_MAX_EDGES + 1) + i];
+    }
+    cnt_out[i] = c;
+    for (int j = 0; j < 4; ++j) sums_out[(size_t)j * (FB_MAX_EDGES + 1) + i] = s[j];
+}
+
 int pk_fetch(fb_plan* p, fb_pk_result* out) {
     const int n = p->nedges + 1;
+    unsigned long long* dc = reinterpret_cast<unsigned long long*>(p->pk_fold);
+    double* ds = reinterpret_cast<double*>(dc + (FB_MAX_EDGES + 1));
+    k_pk_fold<<<(n + 127) / 128, 128, 0, p->stream>>>(p->h_count, p->h_sums, dc, ds, n);
+    FB_LAUNCH_CHECK();
+    const size_t bytes = 5 * (size_t)(FB_MAX_EDGES + 1) * 8;
+    FB_CUDA(cudaMemcpyAsync(p->pk_host, p->pk_fold, bytes, cudaMemcpyDeviceToHost, p->stream));
     FB_CUDA(cudaStreamSynchronize(p->stream));
-    // the device histogram is replicated FB_PK_COPIES times (CTAs spread their reductions over
-    // the copies so that no single L2 address serialises them); sum the copies here
-    const size_t per = (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
-    std::vector<unsigned long long> hc(per);
-    std::vector<double> hs(4 * per);
-    FB_CUDA(cudaMemcpy(hc.data(), p->h_count, per * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    FB_CUDA(cudaMemcpy(hs.data(), p->h_sums, 4 * per * sizeof(double), cudaMemcpyDeviceToHost));
+    const unsigned long long* hc = reinterpret_cast<const unsigned long long*>(p->pk_host);
+    const double* hs = reinterpret_cast<const double*>(hc + (FB_MAX_EDGES + 1));
     double* dst[4] = {out->sum1, out->sum2, out->sum_l2, out->sum_l4};
     for (int i = 0; i < n; ++i) {
-        if (out->count) {
-            unsigned long long c = 0;
-            for (int k = 0; k < FB_PK_COPIES; ++k) c += hc[(size_t)k * (FB_MAX_EDGES + 1) + i];
-            out->count[i] = c;
-        }
+        if (out->count) out->count[i] = hc[i];
         for (int j = 0; j < 4; ++j)
-            if (dst[j]) {
-                double s = 0.0;
-                for (int k = 0; k < FB_PK_COPIES; ++k) s += hs[(size_t)j * per + (size_t)k * (FB_MAX_EDGES + 1) + i];
-                dst[j][i] = s;
-            }
+            if (dst[j]) dst[j][i] = hs[(size_t)j * (FB_MAX_EDGES + 1) + i];
     }
     return 0;
 }
@@ -250,6 +261,8 @@ int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int de
     FB_CUDA(cudaMalloc((void**)&p->thr, FB_MAX_EDGES * sizeof(double)));
     FB_CUDA(cudaMalloc((void**)&p->h_count, FB_PK_COPIES * (FB_MAX_EDGES + 1) * sizeof(unsigned long long)));
     FB_CUDA(cudaMalloc((void**)&p->h_sums, 4 * FB_PK_COPIES * (FB_MAX_EDGES + 1) * sizeof(double)));
+    FB_CUDA(cudaMalloc(&p->pk_fold, 5 * (FB_MAX_EDGES + 1) * 8));
+    FB_CUDA(cudaMallocHost(&p->pk_host, 5 * (FB_MAX_EDGES + 1) * 8));
     FB_CUDA(cudaMalloc((void**)&p->scal, 8 * sizeof(double)));
     FB_CUDA(cudaMallocHost((void**)&p->scal_host, 8 * sizeof(double)));
     for (int i = 0; i < 8; ++i) FB_CUDA(cudaEventCreate(&p->ev[i]));
@@ -267,6 +280,8 @@ int fb_plan_destroy(fb_plan* p) {
     cudaFree(p->h_count);
     cudaFree(p->h_sums);
     cudaFree(p->scal);
+    cudaFree(p->pk_fold);
+    cudaFreeHost(p->pk_host);
     cudaFreeHost(p->scal_host);
     cudaFree(p->sqrtp);
     cudaFree(p->tperp);

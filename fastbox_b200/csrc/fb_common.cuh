@@ -110,6 +110,8 @@ struct fb_plan {
     void* pinned;           // pinned bounce buffer for pageable host memory
     size_t pinned_bytes;
     unsigned long long* h_count;
+    void* pk_fold;          // device: folded histogram (count + 4 sums)
+    void* pk_host;          // pinned copy
     double* h_sums;         // 4 arrays of FB_MAX_EDGES+1
     double* scal;           // device scalars [8]
     double* scal_host;      // pinned
