@@ -174,6 +174,8 @@ fb::KSpace fb_plan::kspace() const {
     K.bt_shift = 23 - (int)dlog2s;                       // mode 3: dlog2s carries M, log2s0 carries the base index
     K.bt_base = (int)log2s0;
     K.bt_scale = 1.0f / (float)(1u << (K.bt_shift > 0 && K.bt_shift < 24 ? K.bt_shift : 1));
+    K.bt_mask = (1u << (K.bt_shift > 0 && K.bt_shift < 24 ? K.bt_shift : 1)) - 1u;
+    K.sqrtp_pairs = sqrtp_pairs;
     K.tperp = tperp;
     K.tpar = tpar;
     K.tdense = tdense;
@@ -284,6 +286,7 @@ int fb_plan_destroy(fb_plan* p) {
     cudaFreeHost(p->pk_host);
     cudaFreeHost(p->scal_host);
     cudaFree(p->sqrtp);
+    cudaFree(p->sqrtp_pairs);
     cudaFree(p->tperp);
     cudaFree(p->tpar);
     cudaFree(p->tdense);
@@ -344,6 +347,13 @@ int fb_device_info(int device, char* name, int name_len, int* sm_count, size_t* 
     return 0;
 }
 
+__global__ void k_sqrtp_pairs(const float* __restrict__ t, float2* __restrict__ out, long n, float scale) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float t0 = t[i], t1 = t[i + 1 < n ? i + 1 : i];
+    out[i] = make_float2(t0, (t1 - t0) * scale);         // scale is a power of two: the product stays exact
+}
+
 static int upload_table(float** slot, size_t* cap, const float* host, size_t n) {
     if (!host) {
         if (*slot) FB_CUDA(cudaFree(*slot));
@@ -377,6 +387,20 @@ int fb_set_sqrt_pk(fb_plan* p, const float* table, long n, int mode, double log2
     p->sqrtp_n = n;
     p->log2s0 = log2s0;
     p->dlog2s = dlog2s;
+    if (mode == 3) {
+        if (p->sqrtp_pairs_cap < (size_t)n) {
+            if (p->sqrtp_pairs) FB_CUDA(cudaFree(p->sqrtp_pairs));
+            p->sqrtp_pairs = nullptr;
+            p->sqrtp_pairs_cap = 0;
+            FB_CUDA(cudaMalloc((void**)&p->sqrtp_pairs, (size_t)n * sizeof(float2)));
+            p->sqrtp_pairs_cap = (size_t)n;
+        }
+        const int shift = 23 - (int)dlog2s;
+        k_sqrtp_pairs<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(p->sqrtp, p->sqrtp_pairs, n,
+                                                                          1.0f / (float)(1u << shift));
+        FB_LAUNCH_CHECK();
+        FB_CUDA(cudaStreamSynchronize(p->stream));
+    }
     return 0;
 }
 

@@ -54,11 +54,13 @@ struct KSpace {
     float two_pi_over_lx, two_pi_over_ly, two_pi_over_lz;
     // sqrt(P) table
     const float* sqrtp;
+    const float2* sqrtp_pairs;  // mode 3: (t[i], (t[i+1]-t[i]) * 2^-shift)
     int sqrtp_mode;         // 0 none, 1 integer |m|^2 LUT, 2 log2(s) table
     int sqrtp_n;
     float log2s0, inv_dlog2s;
     int bt_shift, bt_base;  // mode 3: index = (float_bits(s) >> bt_shift) - bt_base
     float bt_scale;         //         fraction = low bits * bt_scale
+    unsigned bt_mask;       //         low bits = float_bits(s) & bt_mask
     // filter
     const float* tperp;     // [(N/2+1)*N]
     const float* tpar;      // [N]
@@ -97,6 +99,8 @@ struct fb_plan {
     int nedges;
     double bin_l0, bin_inv_d;
     float* sqrtp;
+    float2* sqrtp_pairs;
+    size_t sqrtp_pairs_cap;
     int sqrtp_mode;
     long sqrtp_n;
     double log2s0, dlog2s;

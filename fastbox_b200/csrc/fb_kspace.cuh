@@ -23,16 +23,19 @@ __device__ __forceinline__ float sqrtp_logtable(const KSpace& K, float s) {
 }
 
 // sqrt(P) from a table indexed by the leading bits of float(s) (exponent + M mantissa bits) with
-// linear interpolation inside the segment: geometric node spacing without a log2, two adjacent
-// loads (L1 resident), ~10 instructions.  Validated on the host like the log2 table.
-__device__ __forceinline__ float sqrtp_bittable(const KSpace& K, float s) {
-    if (!(s > 0.f)) return 0.f;                          // nan_to_num(P(0)) = 0, box.py:167
+// linear interpolation inside the segment: geometric node spacing without a log2.  The device
+// table holds (node value, slope per mantissa step) pairs, so a lookup is one 8-byte load (L1
+// resident) and one FFMA.  Validated on the host like the log2 table.  The _nz form does not
+// special-case s = 0 (callers zero the k = 0 mode themselves).
+__device__ __forceinline__ float sqrtp_bittable_nz(const KSpace& K, float s) {
     const unsigned key = __float_as_uint(s);
     int i = (int)(key >> K.bt_shift) - K.bt_base;
     i = max(0, min(i, K.sqrtp_n - 2));
-    const float frac = (float)(key & ((1u << K.bt_shift) - 1u)) * K.bt_scale;
-    const float t0 = __ldg(&K.sqrtp[i]), t1 = __ldg(&K.sqrtp[i + 1]);
-    return fmaf(frac, t1 - t0, t0);
+    const float2 tp = __ldg(&K.sqrtp_pairs[i]);
+    return fmaf((float)(key & K.bt_mask), tp.y, tp.x);
+}
+__device__ __forceinline__ float sqrtp_bittable(const KSpace& K, float s) {
+    return s > 0.f ? sqrtp_bittable_nz(K, s) : 0.f;      // nan_to_num(P(0)) = 0, box.py:167
 }
 
 // real multiplier for mode (a,b,c) (global indices); `cf` = index used for the k_par /

@@ -208,12 +208,23 @@ __device__ __forceinline__ void run_amp(const KSpace& K, int flags, int kind, in
             }
         } else {
             const float sab = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2;
-            const bool bits = K.sqrtp_mode == 3;
+            float sv[P];
 #pragma unroll
             for (int e = 0; e < P; ++e) {
                 const int mc = half < 0 ? mode_number(c0 + e, N) : c0 + e + moff;
-                const float sv = sab + (float)(mc * mc) * K.inv_lz2;
-                amp[e] *= bits ? sqrtp_bittable(K, sv) : sqrtp_logtable(K, sv);
+                sv[e] = sab + (float)(mc * mc) * K.inv_lz2;
+            }
+            if (K.sqrtp_mode == 3) {                     // branch-free inner loops; k = 0 is fixed up below
+#pragma unroll
+                for (int e = 0; e < P; ++e) amp[e] *= sqrtp_bittable_nz(K, sv[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < P; ++e) amp[e] *= sqrtp_logtable(K, sv[e]);
+            }
+            if (ma == 0 && mb == 0) {
+#pragma unroll
+                for (int e = 0; e < P; ++e)
+                    if (!(sv[e] > 0.f)) amp[e] = 0.f;    // nan_to_num(P(0)) = 0, box.py:167
             }
         }
     }
