@@ -110,6 +110,12 @@ __device__ __forceinline__ int pk_bin_g(const KSpace& K, const double* __restric
     while (g > 0 && s < thr[g - 1]) --g;
     return g;
 }
+// same, starting from a nearby bin (the other end of a short run)
+__device__ __forceinline__ int pk_bin_near(const KSpace& K, const double* __restrict__ thr, double s, int g) {
+    while (g < K.nedges && s >= thr[g]) ++g;
+    while (g > 0 && s < thr[g - 1]) --g;
+    return g;
+}
 
 // per-CTA shared-memory copies of the float64 tables the binning needs.  (Per-lane strided reads
 // of these through L1 cost 32 sector look-ups per warp request and dominated the kernel.)
@@ -124,7 +130,13 @@ struct PkSmem {
 };
 template <int N>
 __device__ __forceinline__ PkTables pk_stage_tables(const KSpace& K, double* sm) {
-    for (int c = threadIdx.x; c < N; c += blockDim.x) sm[c + (c >> 4)] = __ldg(&K.az[c]);
+    const double2* az2 = reinterpret_cast<const double2*>(K.az);
+    for (int c = 2 * threadIdx.x; c < N; c += 2 * blockDim.x) {       // pairs never straddle a pad
+        const double2 v = __ldg(az2 + (c >> 1));
+        double* d = sm + c + (c >> 4);
+        d[0] = v.x;
+        d[1] = v.y;
+    }
     double* thr = sm + PkSmem<N>::AZ;
     for (int j = threadIdx.x; j < K.nedges; j += blockDim.x) thr[j] = __ldg(&K.thr[j]);
     PkTables t;
@@ -277,7 +289,7 @@ __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, cons
     const double* az = tb.az + c0 + (c0 >> 4);           // (m_c/Lz)^2, shared memory, padded every 16
     const double* thr = tb.thr;
     const double s_first = __dadd_rn(sab, az[0]), s_last = __dadd_rn(sab, az[P - 1]);
-    const int b0 = pk_bin_g(K, thr, s_first), b1 = pk_bin_g(K, thr, s_last);
+    const int b0 = pk_bin_g(K, thr, s_first), b1 = MONOTONE ? pk_bin_near(K, thr, s_last, b0) : pk_bin_g(K, thr, s_last);
     const int lo = min(b0, b1), hi = max(b0, b1);
     const bool simple = MONOTONE && !poles && (hi - lo <= 1);
     if (__all_sync(full, simple || !rvalid)) {
@@ -389,6 +401,15 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
     float2 v[P];
     PkTables tb;
     if (do_pk) tb = pk_stage_tables<N>(A.K, reinterpret_cast<double*>(smem_raw + G::FFT_SMEM));   // visible after the barrier below
+    // fast path of the prologue (warp-uniform): noise / Philox source, float-bit sqrt(P) table or
+    // none, separable filter or none, plain density field
+    const bool fast = T > 1 && SRC != SRC_SPEC && SRC != SRC_CUBE && A.kind == FB_KIND_PLAIN && !antiherm &&
+                      (!(A.flags & FB_F_SQRTPK) || A.K.sqrtp_mode == 3) && (!(A.flags & FB_F_FILTER) || !A.K.tdense);
+    const int ma_ = mode_number(a, N), mb_ = mode_number(b, N);
+    const float sab_f = (float)(ma_ * ma_) * A.K.inv_lx2 + (float)(mb_ * mb_) * A.K.inv_ly2;
+    const bool dc_row = ma_ == 0 && mb_ == 0;
+    float fast_base = 0.5f;
+    if (fast && (A.flags & FB_F_FILTER)) fast_base *= __ldg(&A.K.tperp[a * N + b]);
 
 #pragma unroll
     for (int j = 0; j < P / 4; ++j) {
@@ -423,6 +444,27 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
                 load_run<4>(A.src + row_m + mq, mm);
                 gm0 = __ldg(&A.src[row_m + cm0]);
             }
+            if (fast) {
+                // common configuration (bit-table sqrt(P), separable or no filter, plain field):
+                // every option test is hoisted out of the per-mode work
+                const int m0 = cq + (j >= P / 8 ? -N : 0);
+                float tf[4] = {1.f, 1.f, 1.f, 1.f};
+                if (A.flags & FB_F_FILTER) load_run<4>(A.K.tpar + cq, tf);
+                if (A.flags & FB_F_SQRTPK) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int mc = m0 + e;
+                        tf[e] *= sqrtp_bittable_nz(A.K, sab_f + (float)(mc * mc) * A.K.inv_lz2);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float am = fast_base * tf[e];
+                    const float2 y = (e == 0) ? gm0 : mm[4 - e];
+                    h[e] = make_float2((g[e].x + y.x) * am, (g[e].y - y.y) * am);
+                }
+                if (dc_row && cq == 0 && (A.flags & FB_F_SQRTPK)) h[0] = make_float2(0.f, 0.f);   // nan_to_num(P(0)) = 0, box.py:167
+            } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float2 x = g[e];
@@ -439,8 +481,10 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
                 }
                 h[e] = antiherm ? make_float2(x.y + y.y, y.x - x.x) : make_float2(x.x + y.x, x.y - y.y);
             }
+            }
         }
         // ---- 2. k-space multiplier
+        if (!fast) {
         float amp[4];
         run_amp<N, 4>(A.K, amp_flags, A.kind, a, b, cq, SRC == SRC_SPEC ? 1.f : 0.5f, amp,
                       (T > 1) ? (j >= P / 8 ? 1 : 0) : -1);
@@ -448,6 +492,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
         for (int e = 0; e < 4; ++e)
             h[e] = velocity ? make_float2(-h[e].y * amp[e], h[e].x * amp[e])      // * i, box.py:254-256
                             : make_float2(h[e].x * amp[e], h[e].y * amp[e]);
+        }
         if (A.spec_out && rvalid) store_run<4>(A.spec_out + row_local + cq, h);
         if constexpr (T > 1) {
             float2* pq = sm + sl(cq);                    // a quad never straddles a pad
