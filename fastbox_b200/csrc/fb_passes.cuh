@@ -26,7 +26,10 @@ struct RowGeom {
     static constexpr int RB = 256 / T;          // rows per CTA (rows are flat over (plane, b))
     static constexpr int THREADS = 256;
     static constexpr size_t FFT_SMEM = (size_t)RB * RowLayout<N>::ROW * sizeof(float2);
-    static constexpr size_t SMEM = FFT_SMEM + (size_t)(N + N / 16 + FB_MAX_EDGES) * sizeof(double);   // + P(k) tables
+    static constexpr size_t PK_SMEM = (size_t)(N + N / 16 + FB_MAX_EDGES) * sizeof(double);           // P(k) tables
+    static constexpr int AMP_ROW = N / 2 + 4;   // floats: sqrt(P) amplitude of modes c = 0..N/2 of one row
+    static constexpr size_t SMEM = FFT_SMEM + PK_SMEM;
+    static constexpr size_t SMEM_INV = SMEM + (T > 1 ? (size_t)RB * AMP_ROW * sizeof(float) : 0);     // rows_inv only
 };
 
 struct RowsArgs {
@@ -411,6 +414,88 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
     float fast_base = 0.5f;
     if (fast && (A.flags & FB_F_FILTER)) fast_base *= __ldg(&A.K.tperp[a * N + b]);
 
+    bool fast_done = false;
+    if constexpr (T > 1 && (SRC == SRC_NOISE || SRC == SRC_PHILOX)) {
+        if (fast) {
+            // Common configuration (bit-table sqrt(P) or none, separable filter or none, plain
+            // field).  The loop body is free of branches (options are predicated loads / selects),
+            // so the loads of later quads are scheduled above the arithmetic of earlier ones.
+            fast_done = true;
+            const bool has_f = (A.flags & FB_F_FILTER) != 0, has_s = (A.flags & FB_F_SQRTPK) != 0;
+            const bool do_store = A.spec_out != nullptr && rvalid;
+            const float4* tpar4 = reinterpret_cast<const float4*>(A.K.tpar);
+            // sqrt(P) depends on |m_c| only: evaluate it once for c = 0..N/2 with consecutive lanes on
+            // consecutive modes (their table entries share a few 32-byte sectors; in quad order every
+            // lane hit its own sector and the L1 data path became the limiter), park it in shared
+            // memory, and read it back in quad order, mirrored for c > N/2.
+            float* amp_row = reinterpret_cast<float*>(smem_raw + G::SMEM) + rl * G::AMP_ROW;
+            if (has_s) {
+#pragma unroll
+                for (int i = 0; i <= P / 2; ++i) {
+                    const int c = t + T * i;
+                    if (i < P / 2 || t == 0) {
+                        float am = sqrtp_bittable_nz(A.K, sab_f + (float)(c * c) * A.K.inv_lz2);
+                        if (i == 0 && dc_row && t == 0) am = 0.f;                 // nan_to_num(P(0)) = 0, box.py:167
+                        amp_row[c] = am;
+                    }
+                }
+                __syncthreads();
+            }
+            const unsigned full = 0xffffffffu;
+            const bool lane_first = (threadIdx.x & 31) == 0 || t == 0;
+#pragma unroll
+            for (int j = 0; j < P / 4; ++j) {
+                const int cq = 4 * t + 4 * T * j;
+                const int mq = N - cq - 4, cm0 = (N - cq) & (N - 1);
+                float2 g[4], mm[4], gm0;
+                if constexpr (SRC == SRC_NOISE) {
+                    float r[4], i[4], rm[4], im[4];
+                    load_run_stream<4>(A.re + row_g + cq, r);
+                    load_run_stream<4>(A.im + row_g + cq, i);
+                    load_run_stream<4>(A.re + row_m + mq, rm);
+                    load_run_stream<4>(A.im + row_m + mq, im);
+                    // the mirror of mode cq is cell N - cq = first cell of the previous lane's mirror block
+                    gm0.x = __shfl_up_sync(full, rm[0], 1);
+                    gm0.y = __shfl_up_sync(full, im[0], 1);
+                    if (lane_first) gm0 = make_float2(__ldg(&A.re[row_m + cm0]), __ldg(&A.im[row_m + cm0]));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        g[e] = make_float2(r[e], i[e]);
+                        mm[e] = make_float2(rm[e], im[e]);
+                    }
+                } else {
+                    philox_mode_pair(A.seed, row_g + cq, row_m + cm0, g[0], gm0);
+#pragma unroll
+                    for (int e = 1; e < 4; ++e)
+                        philox_mode_pair(A.seed, row_g + cq + e, row_m + mq + 4 - e, g[e], mm[4 - e]);
+                    mm[0] = gm0;
+                }
+                const float4 tq = has_f ? __ldg(tpar4 + (cq >> 2)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                float am[4] = {tq.x, tq.y, tq.z, tq.w};
+                if (has_s) {
+                    if (j < P / 8) {                     // c < N/2: amplitudes cq..cq+3
+                        const float4 aq = *reinterpret_cast<const float4*>(amp_row + cq);
+                        am[0] *= aq.x; am[1] *= aq.y; am[2] *= aq.z; am[3] *= aq.w;
+                    } else {                             // c >= N/2: |m_c| = N - c, i.e. amplitudes N-cq, .., N-cq-3
+                        const float4 aq = *reinterpret_cast<const float4*>(amp_row + mq);
+                        am[0] *= amp_row[mq + 4]; am[1] *= aq.w; am[2] *= aq.z; am[3] *= aq.y;
+                    }
+                }
+                float2 h[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float f = fast_base * am[e];
+                    const float2 y = (e == 0) ? gm0 : mm[4 - e];
+                    h[e] = make_float2((g[e].x + y.x) * f, (g[e].y - y.y) * f);
+                }
+                if (do_store) store_run<4>(A.spec_out + row_local + cq, h);
+                float2* pq = sm + sl(cq);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pq[e] = h[e];
+            }
+        }
+    }
+    if (!fast_done) {
 #pragma unroll
     for (int j = 0; j < P / 4; ++j) {
         const int cq = 4 * t + 4 * T * j;              // first mode of this quad
@@ -444,27 +529,6 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
                 load_run<4>(A.src + row_m + mq, mm);
                 gm0 = __ldg(&A.src[row_m + cm0]);
             }
-            if (fast) {
-                // common configuration (bit-table sqrt(P), separable or no filter, plain field):
-                // every option test is hoisted out of the per-mode work
-                const int m0 = cq + (j >= P / 8 ? -N : 0);
-                float tf[4] = {1.f, 1.f, 1.f, 1.f};
-                if (A.flags & FB_F_FILTER) load_run<4>(A.K.tpar + cq, tf);
-                if (A.flags & FB_F_SQRTPK) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int mc = m0 + e;
-                        tf[e] *= sqrtp_bittable_nz(A.K, sab_f + (float)(mc * mc) * A.K.inv_lz2);
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float am = fast_base * tf[e];
-                    const float2 y = (e == 0) ? gm0 : mm[4 - e];
-                    h[e] = make_float2((g[e].x + y.x) * am, (g[e].y - y.y) * am);
-                }
-                if (dc_row && cq == 0 && (A.flags & FB_F_SQRTPK)) h[0] = make_float2(0.f, 0.f);   // nan_to_num(P(0)) = 0, box.py:167
-            } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float2 x = g[e];
@@ -481,10 +545,8 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
                 }
                 h[e] = antiherm ? make_float2(x.y + y.y, y.x - x.x) : make_float2(x.x + y.x, x.y - y.y);
             }
-            }
         }
         // ---- 2. k-space multiplier
-        if (!fast) {
         float amp[4];
         run_amp<N, 4>(A.K, amp_flags, A.kind, a, b, cq, SRC == SRC_SPEC ? 1.f : 0.5f, amp,
                       (T > 1) ? (j >= P / 8 ? 1 : 0) : -1);
@@ -492,7 +554,6 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
         for (int e = 0; e < 4; ++e)
             h[e] = velocity ? make_float2(-h[e].y * amp[e], h[e].x * amp[e])      // * i, box.py:254-256
                             : make_float2(h[e].x * amp[e], h[e].y * amp[e]);
-        }
         if (A.spec_out && rvalid) store_run<4>(A.spec_out + row_local + cq, h);
         if constexpr (T > 1) {
             float2* pq = sm + sl(cq);                    // a quad never straddles a pad
@@ -502,6 +563,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[4 * j + e] = h[e];
         }
+    }
     }
     if (T > 1 || do_pk) __syncthreads();
     // ---- 3. binned moments of |H|^2 (box.py:741-764), run order

@@ -22,9 +22,9 @@ template <int N>
 static int launch_n(fb_plan* p, const RowsArgs& a) {
     using G = RowGeom<N>;
     auto kern = k_rows_inv<N, FB_SRC>;
-    if (set_smem(kern, G::SMEM)) return -2;
+    if (set_smem(kern, G::SMEM_INV)) return -2;
     const long blocks = (a.nrows + G::RB - 1) / G::RB;
-    kern<<<(unsigned)blocks, G::THREADS, G::SMEM, p->stream>>>(a);
+    kern<<<(unsigned)blocks, G::THREADS, G::SMEM_INV, p->stream>>>(a);
     FB_LAUNCH_CHECK();
     return 0;
 }
