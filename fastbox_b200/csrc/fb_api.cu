@@ -236,13 +236,14 @@ int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int de
     FB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     // twiddles exp(-2 pi i m / NMAX), evaluated in double
     {
-        std::vector<float2> tw(FB_NMAX_TW);
-        for (int m = 0; m < FB_NMAX_TW; ++m) {
-            const double ang = -2.0 * M_PI * (double)m / (double)FB_NMAX_TW;
-            tw[m] = make_float2((float)cos(ang), (float)sin(ang));
+        std::vector<float2> tw(FB_TW_ENTRIES, make_float2(1.f, 0.f));
+        for (int n = 1; n <= FB_NMAX_TW; n *= 2)
+        for (int m = 0; m < n; ++m) {
+            const double ang = -2.0 * M_PI * (double)m / (double)n;
+            tw[n + m] = make_float2((float)cos(ang), (float)sin(ang));
         }
-        FB_CUDA(cudaMalloc((void**)&p->tw, FB_NMAX_TW * sizeof(float2)));
-        FB_CUDA(cudaMemcpy(p->tw, tw.data(), FB_NMAX_TW * sizeof(float2), cudaMemcpyHostToDevice));
+        FB_CUDA(cudaMalloc((void**)&p->tw, FB_TW_ENTRIES * sizeof(float2)));
+        FB_CUDA(cudaMemcpy(p->tw, tw.data(), FB_TW_ENTRIES * sizeof(float2), cudaMemcpyHostToDevice));
     }
     // per-axis (m/L)^2 in float64: same two roundings as NumPy's (K/L)**2. (box.py:125-127)
     {

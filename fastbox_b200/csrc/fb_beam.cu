@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_r2c(const float* _
         const int k = t + T * q;
         const float2 zk = v[q];
         const float2 zm = cconj(sm[sl((M - k) & (M - 1))]);
-        const float2 w = __ldg(&tw[k * (FB_NMAX_TW / NF)]);      // e^{-2 pi i k / 2N}
+        const float2 w = FB_TW(tw, NF, k);      // e^{-2 pi i k / 2N}
         const float2 sp = cadd(zk, zm), df = cmul(csub(zk, zm), w);
         dst[(size_t)k * N] = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));
         if (k == 0) dst[(size_t)M * N] = make_float2(zk.x - zk.y, 0.f);
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_c2r(const float2* 
         const int k = t + T * q;
         const float2 xk = v[q];
         const float2 xm = cconj(k == 0 ? xnyq : sm[sl(M - k)]);
-        float2 w = __ldg(&tw[k * (FB_NMAX_TW / NF)]);
+        float2 w = FB_TW(tw, NF, k);
         w.y = -w.y;
         const float2 sp = cadd(xk, xm), df = cmul(csub(xk, xm), w);
         v[q] = make_float2(sp.x - df.y, sp.y + df.x);

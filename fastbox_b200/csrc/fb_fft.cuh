@@ -14,7 +14,12 @@
 
 namespace fb {
 
-#define FB_NMAX_TW 4096      // master twiddle table length (forward sign), owned by the plan
+#define FB_NMAX_TW 4096      // longest transform the twiddle tables cover
+// The plan owns 2*FB_NMAX_TW entries (forward sign): the table of every power-of-two length n sits at
+// [n, 2n), so w_n^k = tw[n + k].  Lanes with consecutive k read consecutive entries (a subsampled
+// master table made each lane hit its own 32-byte sector, which saturated the L1 data path).
+#define FB_TW_ENTRIES (2 * FB_NMAX_TW)
+#define FB_TW(tw, n, k) FB_LDG(&(tw)[(n) + (k)])
 
 // FB_DEV functions also compile for the host so the CPU unit test (tests/host_fft_check.cu)
 // can run the exact index logic thread by thread.
@@ -154,13 +159,12 @@ FB_DEV void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
         for (int r = 0; r < R; ++r) a[r] = v[u + r * B];
         if constexpr (Ns > 1) {
             const int jm = (t + u * T) & (Ns - 1);
-            constexpr int step = (FB_NMAX_TW / (Ns * R));
-            if constexpr (R >= 8) {
+            if constexpr (R >= 4) {
                 // twiddles w^r, r = 1..R-1, from ONE table load: powers by a product tree of depth
                 // <= 4 (each lane's R-1 twiddles are distinct, so loading them all costs ~R sector
                 // look-ups per lane in L1 -- far more than the data itself)
                 float2 w[R];
-                w[1] = FB_LDG(&tw[jm * step]);
+                w[1] = FB_TW(tw, Ns * R, jm);
                 if (S > 0) w[1].y = -w[1].y;
 #pragma unroll
                 for (int r = 2; r < R; ++r) w[r] = cmul(w[r / 2], w[r - r / 2]);
@@ -169,7 +173,7 @@ FB_DEV void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
             } else {
 #pragma unroll
                 for (int r = 1; r < R; ++r) {
-                    float2 w = FB_LDG(&tw[r * jm * step]);
+                    float2 w = FB_TW(tw, Ns * R, r * jm);
                     if (S > 0) w.y = -w.y;
                     a[r] = cmul(a[r], w);
                 }

@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
         const int k = t + T * q;
         const float2 xk = v[q];
         const float2 xm = cconj(k == 0 ? xnyq : sm[sl(M - k)]);
-        float2 w = __ldg(&A.tw[k * (FB_NMAX_TW / N)]);
+        float2 w = FB_TW(A.tw, N, k);
         w.y = -w.y;                                    // e^{+2 pi i k / N}
         const float2 sp = cadd(xk, xm), df = cmul(csub(xk, xm), w);
         v[q] = make_float2(sp.x - df.y, sp.y + df.x);  // sp + i*df
@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
         const int k = t + T * q;
         const float2 zk = v[q];
         const float2 zm = cconj(sm[sl((M - k) & (M - 1))]);
-        const float2 w = __ldg(&A.tw[k * (FB_NMAX_TW / N)]);      // e^{-2 pi i k / N}
+        const float2 w = FB_TW(A.tw, N, k);      // e^{-2 pi i k / N}
         const float2 sp = cadd(zk, zm), df = cmul(csub(zk, zm), w);
         // 1/2 (sp - i df)
         dst[(size_t)k * A.ncols] = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));

@@ -61,10 +61,11 @@ static int check() {
 }
 
 int main() {
-    g_tw.resize(FB_NMAX_TW);
-    for (int m = 0; m < FB_NMAX_TW; ++m) {
-        const double ang = -2.0 * M_PI * m / FB_NMAX_TW;
-        g_tw[m] = make_float2((float)cos(ang), (float)sin(ang));
+    g_tw.assign(FB_TW_ENTRIES, make_float2(1.f, 0.f));
+    for (int len = 1; len <= FB_NMAX_TW; len *= 2)
+    for (int m = 0; m < len; ++m) {
+        const double ang = -2.0 * M_PI * m / len;
+        g_tw[len + m] = make_float2((float)cos(ang), (float)sin(ang));
     }
     int bad = 0;
     bad |= check<4>();
