@@ -240,22 +240,54 @@ __global__ void __launch_bounds__(256) k_exp_sum_f64(const float* __restrict__ d
     block_sum2(acc, 0.0, sums);
 }
 
+// Four consecutive voxels per thread: 16-byte loads / stores and four independent float64 chains
+// (the inversion is a long dependent sequence of correctly rounded operations; one voxel per
+// thread left the kernel waiting on its own latency).  n % 4 == 0 and N % 4 == 0 (N is a power of two >= 4).
 __global__ void __launch_bounds__(256) k_halo_counts(const float* __restrict__ delta, const float* __restrict__ nbar,
                                                       int nbar_kind, const float* __restrict__ bias, int bias_kind,
                                                       int lognormal, double mean_exp, double voxel_vol,
                                                       const double* __restrict__ uniforms, int N, size_t n,
                                                       int32_t* __restrict__ counts, float* __restrict__ mean_out) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double b = (double)(bias_kind == 0 ? bias[0] : (bias_kind == 1 ? bias[i % N] : bias[i]));
-        const double nb = (double)(nbar_kind == 0 ? nbar[0] : (nbar_kind == 1 ? nbar[i % N] : nbar[i]));
-        double dh = __dmul_rn(b, (double)delta[i]);                       // halos.py:104
-        if (lognormal) dh = __dadd_rn(__ddiv_rn(exp(dh), mean_exp), -1.0);  // halos.py:106-108
-        double lam = __dmul_rn(__dmul_rn(voxel_vol, nb), __dadd_rn(1.0, dh));   // halos.py:111
-        if (!lognormal && lam < 0.0) lam = 0.0;                           // halos.py:112-113
-        if (lam != lam) lam = 0.0;                                         // nan_to_num, halos.py:116
-        if (mean_out) mean_out[i] = (float)lam;
-        if (counts) counts[i] = fb_poisson_inv(lam, uniforms[i]);
+    const size_t n4 = n / 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+        const size_t i = 4 * q;
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(delta) + q);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        float bf[4], nf[4];
+        if (bias_kind == 0) {
+            bf[0] = bf[1] = bf[2] = bf[3] = bias[0];
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(bias_kind == 1 ? bias + (i % N) : bias + i));
+            bf[0] = v.x; bf[1] = v.y; bf[2] = v.z; bf[3] = v.w;
+        }
+        if (nbar_kind == 0) {
+            nf[0] = nf[1] = nf[2] = nf[3] = nbar[0];
+        } else {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(nbar_kind == 1 ? nbar + (i % N) : nbar + i));
+            nf[0] = v.x; nf[1] = v.y; nf[2] = v.z; nf[3] = v.w;
+        }
+        double lam[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double dh = __dmul_rn((double)bf[e], (double)d[e]);                 // halos.py:104
+            if (lognormal) dh = __dadd_rn(__ddiv_rn(exp(dh), mean_exp), -1.0);  // halos.py:106-108
+            double l = __dmul_rn(__dmul_rn(voxel_vol, (double)nf[e]), __dadd_rn(1.0, dh));   // halos.py:111
+            if (!lognormal && l < 0.0) l = 0.0;                                 // halos.py:112-113
+            if (l != l) l = 0.0;                                                // nan_to_num, halos.py:116
+            lam[e] = l;
+        }
+        if (mean_out)
+            reinterpret_cast<float4*>(mean_out)[q] = make_float4((float)lam[0], (float)lam[1], (float)lam[2], (float)lam[3]);
+        if (counts) {
+            const double2 u01 = __ldg(reinterpret_cast<const double2*>(uniforms) + 2 * q);
+            const double2 u23 = __ldg(reinterpret_cast<const double2*>(uniforms) + 2 * q + 1);
+            const double u[4] = {u01.x, u01.y, u23.x, u23.y};
+            int32_t k[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) k[e] = fb_poisson_inv(lam[e], u[e]);
+            reinterpret_cast<int4*>(counts)[q] = make_int4(k[0], k[1], k[2], k[3]);
+        }
     }
 }
 
@@ -391,9 +423,10 @@ int fb_halo_counts(fb_plan* p, const float* delta, const float* nbar, int nbar_k
     const void *dd = nullptr, *dnb = nullptr, *dbi = nullptr, *du = nullptr;
     void *dc = nullptr, *dm = nullptr;
     if (stage_in(p, 0, delta, n3 * sizeof(float), &dd)) return -2;
-    if (ensure_aux(p, (sz[nbar_kind] + sz[bias_kind]) * sizeof(float))) return -2;
+    const size_t nb_slot = (sz[nbar_kind] + 3) & ~(size_t)3;                 // keep both tables 16-byte aligned
+    if (ensure_aux(p, (nb_slot + sz[bias_kind]) * sizeof(float))) return -2;
     float* a_nb = (float*)p->aux;
-    float* a_bi = a_nb + sz[nbar_kind];
+    float* a_bi = a_nb + nb_slot;
     if (is_device_ptr(nbar)) dnb = nbar; else {
         FB_CUDA(cudaMemcpyAsync(a_nb, nbar, sz[nbar_kind] * sizeof(float), cudaMemcpyHostToDevice, p->stream));
         dnb = a_nb;
@@ -405,6 +438,9 @@ int fb_halo_counts(fb_plan* p, const float* delta, const float* nbar, int nbar_k
     if (stage_in(p, 5, uniforms, n3 * sizeof(double), &du)) return -2;
     if (stage_out_begin(p, 1, counts_out, n3 * sizeof(int32_t), &dc)) return -2;
     if (stage_out_begin(p, 2, mean_out, n3 * sizeof(float), &dm)) return -2;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    FB_CHECK(al16(dd) && al16(du) && al16(dc) && al16(dm) && (nbar_kind == 0 || al16(dnb)) && (bias_kind == 0 || al16(dbi)),
+             "fb_halo_counts: device buffers must be 16-byte aligned");
     if (lognormal && !(mean_exp > 0.0)) {
         FB_CUDA(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
         k_exp_sum_f64<<<grid_for(n3, 256, p->sm_count), 256, 0, p->stream>>>((const float*)dd, (const float*)dbi,
@@ -415,7 +451,7 @@ int fb_halo_counts(fb_plan* p, const float* delta, const float* nbar, int nbar_k
         mean_exp = p->scal_host[0] / (double)n3;
     }
     const double vol = p->Lx * p->Ly * p->Lz / pow((double)N, 3.0);        // halos.py:101
-    k_halo_counts<<<grid_for(n3, 256, p->sm_count), 256, 0, p->stream>>>(
+    k_halo_counts<<<grid_for(n3 / 4, 256, p->sm_count), 256, 0, p->stream>>>(
         (const float*)dd, (const float*)dnb, nbar_kind, (const float*)dbi, bias_kind, lognormal, mean_exp, vol,
         (const double*)du, N, n3, (int32_t*)dc, (float*)dm);
     FB_LAUNCH_CHECK();
