@@ -61,6 +61,7 @@ SIGNATURES = {
     "fb_rsd_remap": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp]),
     "fb_beam_convolve": (_i, [_vp, _vp, _vp, _vp]),
     "fb_halo_counts": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
+    "fb_halo_catalogue": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_c2r_gather": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
@@ -292,6 +293,13 @@ class Plan(object):
         check(self.lib.fb_halo_counts(self.h, _ptr(delta), _ptr(nbar), int(nbar_kind), _ptr(bias), int(bias_kind),
                                       int(bool(lognormal)), float(mean_exp), _ptr(uniforms), _ptr(counts_out),
                                       _ptr(mean_out)))
+
+    def halo_catalogue(self, counts, uniforms=None, cat_out=None, capacity=0):
+        """Rows of the catalogue of `counts` (int32 [N^3]); with cat_out (float64 [capacity][3]) also fills it."""
+        nh = _u64(0)
+        check(self.lib.fb_halo_catalogue(self.h, _ptr(counts), _ptr(uniforms), _ptr(cat_out), int(capacity),
+                                         C.byref(nh)))
+        return int(nh.value)
 
     def fft_pass_c2c(self, data, nplanes, axis_pass, sign):
         check(self.lib.fb_fft_pass_c2c(self.h, _ptr(data), int(nplanes), int(axis_pass), int(sign)))

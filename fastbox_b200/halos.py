@@ -1,6 +1,7 @@
 """
 Poisson halo / galaxy counts on top of a density field (reference
-``fastbox/halos.py``).  ``halo_count_field`` (halos.py:53-117) runs on the device.
+``fastbox/halos.py``).  ``halo_count_field`` (halos.py:53-117) and
+``realise_halo_catalogue`` (halos.py:120-176) run on the device.
 """
 import numpy as np
 
@@ -53,21 +54,40 @@ class HaloDistribution(object):
             return counts.astype(np.int64), mean
         return counts.astype(np.int64)
 
-    def realise_halo_catalogue(self, Nhalo, scatter=False, scatter_type='uniform'):
-        """Counts -> comoving positions (halos.py:120-176); host side (not on the hot path)."""
-        Nhalo = np.asarray(Nhalo)
-        idx = np.nonzero(Nhalo > 0)
-        reps = Nhalo[idx]
-        order = np.argsort(reps, kind="stable")         # reference groups voxels by count value
-        cat = np.column_stack([np.repeat(ax[order], reps[order]) for ax in idx]).astype(np.float64)
+    def realise_halo_catalogue(self, Nhalo, scatter=False, scatter_type='uniform', uniforms=None):
+        """
+        Counts per voxel -> catalogue of comoving positions, shape (Nhalos, 3)
+        (halos.py:120-176), built on the device (``fb_halo_catalogue``: per-tile
+        histograms, exclusive scan, stable scatter).  Row order is the reference's:
+        ascending count value, then C-order voxel index, every voxel repeated
+        ``count`` times.  With ``scatter=True`` the offsets are
+        ``np.random.uniform(0, 1-1e-8, 3*Nhalos)`` drawn exactly as the reference
+        draws them (halos.py:166), or ``uniforms`` (Nhalos, 3) if given, so the
+        catalogue is bit-identical to the reference's under the same seed.
+        """
+        if scatter and scatter_type != 'uniform':
+            raise ValueError("scatter_type='%s' not recognised" % scatter_type)
+        box = self.box
+        N = box.N
+        plan = box._plan
+        cnt = np.asarray(Nhalo)
+        if cnt.shape != (N, N, N):
+            raise ValueError("Nhalo must have shape (N, N, N)")
+        if cnt.size and (cnt.min() < 0 or cnt.max() > np.iinfo(np.int32).max):
+            raise ValueError("halo counts must be non-negative 32-bit integers")
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        nh = plan.halo_catalogue(cnt)
+        cat = np.empty((nh, 3), dtype=np.float64)
+        if nh == 0:
+            return cat
+        u = None
         if scatter:
-            if scatter_type == 'uniform':
-                cat += np.random.uniform(0., 1. - 1e-8, cat.size).reshape(cat.shape)
-            else:
-                raise ValueError("scatter_type='%s' not recognised" % scatter_type)
-        cat[:, 0] *= box_len(self.box.Lx, self.box.N)
-        cat[:, 1] *= box_len(self.box.Ly, self.box.N)
-        cat[:, 2] *= box_len(self.box.Lz, self.box.N)
+            if uniforms is None:
+                uniforms = np.random.uniform(0., 1. - 1e-8, cat.size).reshape(cat.shape)
+            u = np.ascontiguousarray(uniforms, dtype=np.float64)
+            if u.shape != cat.shape:
+                raise ValueError("uniforms must have shape (Nhalos, 3) = %s" % (cat.shape,))
+        plan.halo_catalogue(cnt, u, cat, nh)
         return cat
 
 

@@ -160,6 +160,14 @@ int fb_halo_counts(fb_plan* plan, const float* delta, const float* nbar, int nba
                    int bias_kind, int lognormal, double mean_exp, const double* uniforms, int32_t* counts_out,
                    float* mean_out);
 
+/* ---- halo catalogue: halos.py:120-176 ------------------------------------------ */
+/* counts[N^3] (int32, >= 0, < 1024) -> cat[nhalo][3] float64 comoving positions in the reference's order
+ * (ascending count value, then C-order voxel index, each voxel repeated `count` times).
+ * uniforms: NULL (no scatter) or [nhalo][3] U[0,1) offsets in catalogue order (halos.py:163-166).
+ * cat_out == NULL: only *nhalo_out is set (size query).  capacity = rows cat_out can hold. */
+int fb_halo_catalogue(fb_plan* plan, const int32_t* counts, const double* uniforms, double* cat_out,
+                      uint64_t capacity, uint64_t* nhalo_out);
+
 /* ---- building blocks exposed for tests / multi-GPU orchestration ---------------- */
 /* pass = 0: rows (z, contiguous) c2c; 1: columns (y) c2c; sign = -1 fwd / +1 inv;
  * data: [nplanes][N][N] complex64, in place.                                   */

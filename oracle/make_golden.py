@@ -100,10 +100,38 @@ def run_case(c):
     return out
 
 
+def run_catalogue():
+    """HaloDistribution.realise_halo_catalogue of the unmodified reference (halos.py:120-176)."""
+    box_m = ref_loader.load("box")
+    halos_m = ref_loader.load("halos")
+    out = {}
+    for name, N, scale, lam in (("sparse", 16, (1.0, 0.5, 0.25), 0.05), ("dense", 8, 0.1, 3.0), ("mixed", 32, 0.3, 0.4)):
+        box = box_m.CosmoBox(cosmo=box_m.default_cosmo, box_scale=scale, nsamp=N, redshift=0.4, realise_now=False)
+        hd = halos_m.HaloDistribution(box, (1e12, 1e15), 10)
+        np.random.seed(4242 + N)
+        counts = np.random.poisson(lam=lam, size=(N, N, N))
+        if name == "mixed":
+            counts[3, 5, 7] = 40                       # one rich voxel: many distinct count values
+            counts[31, 31, 31] = 17
+        out[name + "_counts"] = counts.astype(np.int32)
+        out[name + "_L"] = np.array([box.Lx, box.Ly, box.Lz])
+        out[name + "_cat"] = hd.realise_halo_catalogue(counts, scatter=False)
+        np.random.seed(99 + N)
+        out[name + "_cat_scatter"] = hd.realise_halo_catalogue(counts, scatter=True)
+        out[name + "_scatter_seed"] = 99 + N
+    return out
+
+
 def main():
     warnings.simplefilter("ignore")
     dest = os.path.join(ROOT, "tests", "golden")
     os.makedirs(dest, exist_ok=True)
+    if "--catalogue" in sys.argv or "--all" in sys.argv:
+        path = os.path.join(dest, "halo_catalogue.npz")
+        np.savez_compressed(path, **run_catalogue())
+        print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024.))
+        if "--all" not in sys.argv:
+            return
     for c in CASES:
         out = run_case(c)
         path = os.path.join(dest, c["name"] + ".npz")

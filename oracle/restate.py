@@ -459,6 +459,54 @@ def poisson_from_uniform(lam, u, kmax=100000):
     return k
 
 
+def halo_catalogue_port(Nhalo, Lx, Ly, Lz, uniforms=None):
+    """
+    Step-by-step restatement of HaloDistribution.realise_halo_catalogue
+    (halos.py:142-176): loop over the distinct count values (halos.py:146-147),
+    voxels of each value in C order repeated ``count`` times (halos.py:152-155),
+    float64 indices (halos.py:158-160), optional offsets in catalogue order
+    (halos.py:163-166; the reference draws them with np.random.uniform), box scaling
+    (halos.py:172-174).  Pinned against the unmodified reference in
+    tests/golden/halo_catalogue.npz.
+    """
+    Nhalo = np.asarray(Nhalo)
+    N = Nhalo.shape[0]
+    cx, cy, cz = [], [], []
+    for count in np.unique(Nhalo):
+        if count < 1:
+            continue
+        ix, iy, iz = np.where(Nhalo == count)
+        cx.append(np.repeat(ix, count))
+        cy.append(np.repeat(iy, count))
+        cz.append(np.repeat(iz, count))
+    if not cx:
+        return np.empty((0, 3), dtype=np.float64)
+    cat = np.column_stack((np.concatenate(cx), np.concatenate(cy), np.concatenate(cz))).astype(np.float64)
+    if uniforms is not None:
+        cat += np.asarray(uniforms, dtype=np.float64).reshape(cat.shape)
+    cat[:, 0] *= Lx / N
+    cat[:, 1] *= Ly / N
+    cat[:, 2] *= Lz / N
+    return cat
+
+
+def halo_catalogue_lean(Nhalo, Lx, Ly, Lz, uniforms=None):
+    """Same catalogue as a stable sort of the occupied voxels by count (the device algorithm's view)."""
+    Nhalo = np.asarray(Nhalo)
+    N = Nhalo.shape[0]
+    flat = Nhalo.ravel()
+    vox = np.flatnonzero(flat > 0)
+    order = np.argsort(flat[vox], kind="stable")
+    vox = np.repeat(vox[order], flat[vox][order])
+    cat = np.column_stack(np.unravel_index(vox, Nhalo.shape)).astype(np.float64).reshape(-1, 3)
+    if uniforms is not None:
+        cat += np.asarray(uniforms, dtype=np.float64).reshape(cat.shape)
+    cat[:, 0] *= Lx / N
+    cat[:, 1] *= Ly / N
+    cat[:, 2] *= Lz / N
+    return cat
+
+
 # --------------------------------------------------------------------------
 # Counter-based white noise (no reference equivalent: the reference draws
 # from NumPy's global MT19937, box.py:174-175).  Philox4x32-10 keyed by

@@ -149,3 +149,18 @@ def test_philox_known_answer():
     assert [hex(int(x)) for x in out[0]] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
     re, im = R.philox_normals(42, np.arange(64 ** 3), 64)
     assert abs(re.mean()) < 0.01 and abs(re.std() - 1) < 0.01 and abs(np.corrcoef(re, im)[0, 1]) < 0.01
+
+
+@pytest.mark.parametrize("name", ["sparse", "dense", "mixed"])
+def test_halo_catalogue_port_matches_reference_golden(name):
+    """halos.py:120-176: both restatements are bit-identical to the unmodified reference, with and without scatter."""
+    g = load_golden("halo_catalogue")
+    counts, L = g[name + "_counts"], g[name + "_L"]
+    for f in (R.halo_catalogue_port, R.halo_catalogue_lean):
+        cat = f(counts, *L)
+        assert cat.dtype == np.float64 and cat.shape == (counts.sum(), 3)
+        assert np.array_equal(cat, g[name + "_cat"])
+        np.random.seed(int(g[name + "_scatter_seed"]))
+        u = np.random.uniform(0., 1. - 1e-8, cat.size).reshape(cat.shape)       # halos.py:166
+        assert np.array_equal(f(counts, *L, uniforms=u), g[name + "_cat_scatter"])
+    assert R.halo_catalogue_port(np.zeros((4, 4, 4), int), 1., 1., 1.).shape == (0, 3)

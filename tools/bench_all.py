@@ -93,6 +93,11 @@ def main():
     bias = np.array([1.0], np.float32)
     add("halo counts (Poisson inversion)  [a12]", 16,
         timed(plan, lambda: plan.halo_counts(field, nbar, 0, bias, 0, False, 0.0, u, counts), reps=3))
+    # halo catalogue from the counts just drawn: 3 passes over the counts + 24 B per halo
+    nh = plan.halo_catalogue(counts)
+    cat = plan.alloc(max(nh, 1) * 24)
+    ms = timed(plan, lambda: plan.halo_catalogue(counts, None, cat, nh), reps=3)
+    add("halo catalogue, %.1f M halos  [f1]" % (nh / 1e6), 12 + 24.0 * nh / n3, ms)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(dict(N=N, hbm_peak_GBs=peak, rows=rows), open(os.path.join(ROOT, "gpurun_out", "bench_all_%d.json" % N),
                                                             "w"), indent=1)
