@@ -36,10 +36,11 @@ __global__ void __launch_bounds__(256) k_cat_max(const int32_t* __restrict__ cou
                                                   int* __restrict__ mn) {
     int hi = 0, lo = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int c = __ldg(&counts[i]);
-        hi = max(hi, c);
-        lo = min(lo, c);
+    const int4* c4 = reinterpret_cast<const int4*>(counts);          // n = N^3 is a multiple of 4
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
+        const int4 c = __ldg(&c4[i]);
+        hi = max(max(hi, c.x), max(c.y, max(c.z, c.w)));
+        lo = min(min(lo, c.x), min(c.y, min(c.z, c.w)));
     }
     hi = __reduce_max_sync(0xffffffffu, hi);
     lo = __reduce_min_sync(0xffffffffu, lo);
@@ -107,9 +108,12 @@ __global__ void __launch_bounds__(CAT_THREADS) k_cat_tiles(const int32_t* __rest
         const unsigned long long* mybase = wbase + (size_t)warp * K;
         const unsigned lt = (1u << lane) - 1u;
         const int nmask = (1 << log2n) - 1;
-#pragma unroll
+        // second walk: the tile is re-read (L1 / L2 hot) instead of holding 16 keys in registers, and the
+        // loop stays rolled -- unrolled it needed 128 registers and halved the streaming rate
+#pragma unroll 1
         for (int c = 0; c < CAT_TILE / CAT_THREADS; ++c) {
-            const int key = keys[c];
+            const size_t vv = v0 + (size_t)c * 32 + lane;
+            const int key = vv < n ? __ldg(&counts[vv]) : 0;
             if (!__any_sync(full, key > 0)) continue;
             const unsigned m = __match_any_sync(full, key);
             uint32_t run = 0;

@@ -21,7 +21,7 @@ for _ in range(reps):
     plan.timer_start()
     plan.beam_convolve(beam, field, out)
     print("beam ms", plan.timer_stop())
-u = plan.alloc(n3 * 8)
+u = plan.upload(np.random.default_rng(1).random(n3)) if len(sys.argv) > 3 else plan.alloc(n3 * 8)
 counts = plan.alloc(n3 * 4)
 nbar = np.array([1e-3], np.float32)
 bias = np.array([1.0], np.float32)
@@ -29,3 +29,12 @@ for _ in range(reps):
     plan.timer_start()
     plan.halo_counts(field, nbar, 0, bias, 0, False, 0.0, u, counts)
     print("halo ms", plan.timer_stop())
+if len(sys.argv) > 3:                                    # catalogue of the counts just drawn
+    plan.affine(field, n3, 0.0, 0.0)
+    plan.halo_counts(field, np.array([float(sys.argv[3])], np.float32), 0, bias, 0, False, 0.0, u, counts)
+    nh = plan.halo_catalogue(counts)
+    cat = plan.alloc(max(nh, 1) * 24)
+    for _ in range(reps):
+        plan.timer_start()
+        plan.halo_catalogue(counts, None, cat, nh)
+        print("catalogue ms", plan.timer_stop(), "halos", nh)
