@@ -171,6 +171,7 @@ __device__ __forceinline__ void pk_red(const PkDev& out, const PkAcc& a, bool po
 // Lanes of a warp hold consecutive runs of one row, so equal bins sit in contiguous lane
 // segments: a segmented inclusive scan (5 shuffle steps, independent of the number of bins)
 // leaves each segment's total in its last lane, which issues the reductions.
+template <bool POLES>
 __device__ __forceinline__ void pk_seg_flush2(const PkDev& out, PkAcc a, PkAcc b, bool valid) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -187,20 +188,27 @@ __device__ __forceinline__ void pk_seg_flush2(const PkDev& out, PkAcc a, PkAcc b
         const unsigned ca = __shfl_up_sync(full, a.cnt, d), cb = __shfl_up_sync(full, b.cnt, d);
         const double a1 = __shfl_up_sync(full, a.s1, d), a2 = __shfl_up_sync(full, a.s2, d);
         const double b1 = __shfl_up_sync(full, b.s1, d), b2 = __shfl_up_sync(full, b.s2, d);
+        double a3 = 0.0, a4 = 0.0, b3 = 0.0, b4 = 0.0;
+        if constexpr (POLES) {
+            a3 = __shfl_up_sync(full, a.l2, d); a4 = __shfl_up_sync(full, a.l4, d);
+            b3 = __shfl_up_sync(full, b.l2, d); b4 = __shfl_up_sync(full, b.l4, d);
+        }
         if (lane - d >= sa) {
             a.cnt += ca;
             a.s1 += a1;
             a.s2 += a2;
+            if constexpr (POLES) { a.l2 += a3; a.l4 += a4; }
         }
         if (lane - d >= sb) {
             b.cnt += cb;
             b.s1 += b1;
             b.s2 += b2;
+            if constexpr (POLES) { b.l2 += b3; b.l4 += b4; }
         }
     }
     const int na = __shfl_down_sync(full, ka, 1), nb = __shfl_down_sync(full, kb, 1);
-    if (ka >= 0 && (lane == 31 || na != ka)) pk_red(out, a, false);
-    if (kb >= 0 && (lane == 31 || nb != kb)) pk_red(out, b, false);
+    if (ka >= 0 && (lane == 31 || na != ka)) pk_red(out, a, POLES);
+    if (kb >= 0 && (lane == 31 || nb != kb)) pk_red(out, b, POLES);
 }
 
 // Per-run multiplier amp[e] for modes c0+e (sqrt(P) LUT, filter, velocity / potential factor).
@@ -294,7 +302,7 @@ __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, cons
     const double s_first = __dadd_rn(sab, az[0]), s_last = __dadd_rn(sab, az[P - 1]);
     const int b0 = pk_bin_g(K, thr, s_first), b1 = MONOTONE ? pk_bin_near(K, thr, s_last, b0) : pk_bin_g(K, thr, s_last);
     const int lo = min(b0, b1), hi = max(b0, b1);
-    const bool simple = MONOTONE && !poles && (hi - lo <= 1);
+    const bool simple = MONOTONE && (hi - lo <= 1);
     if (__all_sync(full, simple || !rvalid)) {
         // s is monotone along the run, so the run splits at one index: the first kx modes (in the
         // direction of increasing s) fall in bin lo, the rest in bin hi.  kx comes from a 4-step
@@ -329,11 +337,39 @@ __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, cons
                 B.s2 = fma(pd, pd, B.s2);
             }
         }
+        if (poles) {
+            // Legendre weights from mu^2 = k_par^2 / k^2 in float32 (relative error 1e-7; the walk path
+            // below keeps the float64 form for the few low-k runs)
+            const int ma = mode_number(a, N), mb = mode_number(b, N);
+            const float sab_f = (float)(ma * ma) * K.inv_lx2 + (float)(mb * mb) * K.inv_ly2;
+#pragma unroll
+            for (int e = 0; e < P; ++e) {
+                const float p = x ? (h[e].x * x[e].x + h[e].y * x[e].y) * invb : (h[e].x * h[e].x + h[e].y * h[e].y) * invb;
+                const int mc = mode_number(c0 + e, N);
+                const float kz2 = (float)(mc * mc) * K.inv_lz2, sf = sab_f + kz2;
+                const float m2 = sf > 0.f ? __fdividef(kz2, sf) : 0.f;
+                const double w2 = (double)(p * (1.5f * m2 - 0.5f));
+                const double w4 = (double)(p * ((35.f * m2 * m2 - 30.f * m2 + 3.f) * 0.125f));
+                if (e >= e_lo && e < e_hi) {
+                    A.l2 += w2;
+                    A.l4 += w4;
+                } else {
+                    B.l2 += w2;
+                    B.l4 += w4;
+                }
+            }
+        }
         A.cnt = (unsigned)kx * wi;
         B.cnt = (unsigned)(P - kx) * wi;
         A.s1 *= (double)wmult; A.s2 *= (double)wmult;
         B.s1 *= (double)wmult; B.s2 *= (double)wmult;
-        pk_seg_flush2(out, A, B, rvalid);
+        if (poles) {
+            A.l2 *= (double)wmult; A.l4 *= (double)wmult;
+            B.l2 *= (double)wmult; B.l4 *= (double)wmult;
+            pk_seg_flush2<true>(out, A, B, rvalid);
+        } else {
+            pk_seg_flush2<false>(out, A, B, rvalid);
+        }
     } else if (rvalid) {
         PkAcc w;
         w.bin = b0;
