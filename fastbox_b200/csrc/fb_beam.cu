@@ -96,6 +96,67 @@ __global__ void __launch_bounds__(CZ * FftCfg<2 * N>::T, 1) k_beam_x(float2* __r
     }
 }
 
+// ---- pass B, role-split variant for large boxes.  grid = (N/CZ, N+1), block = 2*CZ*T(2N).
+// The first CZ*T threads transform the field columns, the other CZ*T the beam columns (whole warps per
+// role), so a thread holds 16 points instead of 32 and a 1024-thread CTA fits an SM (32 warps instead
+// of 16 for the two forward transforms).  The beam spectrum crosses to the field threads through the
+// exchange buffer; the beam warps then only keep the barriers of the inverse transform company.
+// Measured SLOWER than k_beam_x at 1024^3 (one 1024-thread CTA per SM serialises its load / transform /
+// store phases); kept as an opt-in experiment (FB_BEAM_SPLIT=1) and covered by the parity tests.
+template <int N, int CZ>
+__global__ void __launch_bounds__(2 * CZ * FftCfg<2 * N>::T, 1) k_beam_x_split(float2* __restrict__ yf,
+                                                                              const float2* __restrict__ yb,
+                                                                              double* __restrict__ norm,
+                                                                              const float2* __restrict__ tw) {
+    constexpr int NF = 2 * N;
+    using C = FftCfg<NF>;
+    constexpr int P = C::P, T = C::T;
+    static_assert((CZ * T) % 32 == 0, "roles must own whole warps");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    const int role = threadIdx.x / (CZ * T);             // 0 field, 1 beam
+    const int r = threadIdx.x - role * (CZ * T);
+    const int col = r % CZ, t = r / CZ;
+    const int ky = blockIdx.y;
+    const size_t zc = (size_t)blockIdx.x * CZ + col;
+    const size_t plane = (size_t)(N + 1) * N;
+    float2* f = yf + (size_t)ky * N + zc;
+    const float2* src = (role ? yb : yf) + (size_t)ky * N + zc;
+    float2 v[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int x = t + T * q;                         // zero padding for x >= N
+        v[q] = x < N ? src[(size_t)x * plane] : make_float2(0.f, 0.f);
+    }
+    ColLayout<2 * CZ> sl{role * CZ + col};
+    fft_regs<NF, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, tw);
+    __syncthreads();
+    if (role) {
+        if (ky == 0 && t == 0) norm[zc] = (double)v[0].x;            // DC bin = sum_xy beam (beams.py:81)
+        fft_store_natural<NF, P>(v, t, sm, sl);
+    }
+    __syncthreads();
+    if (!role) {
+        ColLayout<2 * CZ> sb{CZ + col};
+        float2 vb[P];
+        fft_exchange_read<NF, P>(vb, t, sm, sb);
+#pragma unroll
+        for (int q = 0; q < P; ++q) v[q] = cmul(v[q], vb[q]);
+    }
+    __syncthreads();
+    if (role) {
+        fft_regs_barriers_only<C::R2, C::R3>();
+        return;
+    }
+    fft_regs<NF, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, tw);
+    constexpr int st = (N - 1) / 2;                      // 'same' crop w.r.t. the first argument
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int xo = t + T * q - st;
+        if (xo >= 0 && xo < N) f[(size_t)xo * plane] = v[q];
+    }
+}
+
 // ---- pass C: y axis c2r with crop and normalisation.  grid = (N/CZ, N), block = CZ*T(N)
 template <int N, int CZ>
 __global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_c2r(const float2* __restrict__ yf,
@@ -145,11 +206,9 @@ __global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_c2r(const float2* 
     }
 }
 
-template <int N>
-static int beam_run(fb_plan* p, const float* beam, const float* field, float* out, float2* yf, float2* yb,
-                    double* norm) {
-    constexpr int CZA = N >= 16 ? 16 : N;            // columns (z) per CTA in the y passes
-    constexpr int CZB = N >= 4 ? 4 : N;
+template <int N, int CZA, int CZB>
+static int beam_run_cz(fb_plan* p, const float* beam, const float* field, float* out, float2* yf, float2* yb,
+                       double* norm) {
     {
         auto kern = k_beam_y_r2c<N, CZA>;
         const size_t smem = (size_t)(N + N / 16) * CZA * sizeof(float2);
@@ -157,7 +216,21 @@ static int beam_run(fb_plan* p, const float* beam, const float* field, float* ou
         kern<<<dim3(N / CZA, N, 2), CZA * FftCfg<N>::T, smem, p->stream>>>(field, beam, yf, yb, p->tw);
         FB_LAUNCH_CHECK();
     }
-    {
+    if constexpr (N >= 512) {
+        if (env_int("FB_BEAM_SPLIT", 0)) {          // measured slower at 1024^3 (32.7 vs 28.8 ms): opt-in
+            auto kern = k_beam_x_split<N, CZB>;
+            const size_t smem = (size_t)(2 * N + 2 * N / 16) * 2 * CZB * sizeof(float2);
+            if (set_smem(kern, smem)) return -2;
+            kern<<<dim3(N / CZB, N + 1), 2 * CZB * FftCfg<2 * N>::T, smem, p->stream>>>(yf, yb, norm, p->tw);
+            FB_LAUNCH_CHECK();
+        } else {
+            auto kern = k_beam_x<N, CZB>;
+            const size_t smem = (size_t)(2 * N + 2 * N / 16) * CZB * sizeof(float2);
+            if (set_smem(kern, smem)) return -2;
+            kern<<<dim3(N / CZB, N + 1), CZB * FftCfg<2 * N>::T, smem, p->stream>>>(yf, yb, norm, p->tw);
+            FB_LAUNCH_CHECK();
+        }
+    } else {
         auto kern = k_beam_x<N, CZB>;
         const size_t smem = (size_t)(2 * N + 2 * N / 16) * CZB * sizeof(float2);
         if (set_smem(kern, smem)) return -2;
@@ -172,6 +245,24 @@ static int beam_run(fb_plan* p, const float* beam, const float* field, float* ou
         FB_LAUNCH_CHECK();
     }
     return 0;
+}
+
+// columns (z) per CTA: y passes CZA, x pass CZB.  Large boxes take narrower tiles so that two or
+// three CTAs share an SM and their load / transform / store phases overlap.
+template <int N>
+static int beam_run(fb_plan* p, const float* beam, const float* field, float* out, float2* yf, float2* yb,
+                    double* norm) {
+    if constexpr (N >= 512) {
+        const int cza = env_int("FB_BEAM_CZA", 8), czb = env_int("FB_BEAM_CZB", 4);
+        if (cza == 8 && czb == 2) return beam_run_cz<N, 8, 2>(p, beam, field, out, yf, yb, norm);
+        if (cza == 8) return beam_run_cz<N, 8, 4>(p, beam, field, out, yf, yb, norm);
+        if (czb == 2) return beam_run_cz<N, 16, 2>(p, beam, field, out, yf, yb, norm);
+        return beam_run_cz<N, 16, 4>(p, beam, field, out, yf, yb, norm);
+    } else {
+        constexpr int CZA = N >= 16 ? 16 : N;
+        constexpr int CZB = N >= 4 ? 4 : N;
+        return beam_run_cz<N, CZA, CZB>(p, beam, field, out, yf, yb, norm);
+    }
 }
 
 }  // namespace fb

@@ -254,6 +254,17 @@ FB_DEV void fft_regs(float2 (&v)[P], int t, float2* sm, const SL& sl,
     }
 }
 
+// The barriers of fft_regs, for warps of a CTA that sit a transform out (they must arrive at the
+// same __syncthreads as the warps that run it).
+template <int R2, int R3>
+FB_DEV void fft_regs_barriers_only() {
+    if constexpr (R2 > 1) {
+        FB_SYNC();
+        if constexpr (R3 > 1) FB_SYNC();
+    }
+    if constexpr (R3 > 1) FB_SYNC();
+}
+
 // compile-time FFT configuration for each supported length
 template <int n>
 struct FftCfg;

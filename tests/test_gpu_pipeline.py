@@ -284,6 +284,33 @@ def test_beam_convolve_vs_oracle(gpu, N):
     plan.close()
 
 
+def test_beam_convolve_large_box_variants(gpu, monkeypatch):
+    """N >= 512 takes the role-split x pass and narrower y tiles: every variant against scipy on single channels."""
+    import scipy.signal
+    N = 512
+    rng = np.random.default_rng(5)
+    field = rng.standard_normal((N, N, N), dtype=np.float32)
+    x = np.arange(N) - N / 2. + 0.5
+    s = 2.0 + 6.0 * np.arange(N) / N
+    beam = (np.exp(-0.5 * (x[:, None, None] ** 2 + (x[None, :, None] - 0.7) ** 2) / s[None, None, :] ** 2)
+            * (1 + 0.1 * np.cos(x[:, None, None]))).astype(np.float32)
+    plan = _lib.Plan(N, 1e3, 1e3, 1e3)
+    outs = {}
+    for split, cza in ((1, 8), (0, 16), (1, 16)):
+        monkeypatch.setenv("FB_BEAM_SPLIT", str(split))
+        monkeypatch.setenv("FB_BEAM_CZA", str(cza))
+        out = np.empty((N, N, N), np.float32)
+        plan.beam_convolve(beam, field, out)
+        outs[(split, cza)] = out
+    for z in (0, 201, N - 1):
+        b2, f2 = beam[:, :, z].astype(np.float64), field[:, :, z].astype(np.float64)
+        ref = scipy.signal.fftconvolve(b2, f2, mode='same') / b2.sum()         # beams.py:81-87, one channel
+        for out in outs.values():
+            assert rel_l2(out[:, :, z], ref) < TOL
+    assert np.array_equal(outs[(1, 8)], outs[(1, 16)])
+    plan.close()
+
+
 @pytest.mark.parametrize("N,vscale", [(64, 5.0), (128, 60.0), (128, 2000.0), (256, 300.0)])
 def test_rsd_remap_large_displacements(gpu, N, vscale):
     """Windowed bracket search == sort-based restatement, incl. periodic wrap-around and shell crossing."""
