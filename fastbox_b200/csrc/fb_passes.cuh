@@ -18,6 +18,9 @@ enum { SRC_NOISE = 0, SRC_PHILOX = 1, SRC_SPEC = 2, SRC_CUBE = 3 };
 #ifndef FB_ROWS_MINB
 #define FB_ROWS_MINB 3      // CTAs per SM the row kernels are compiled for (register cap 65536/(256*MINB))
 #endif
+#ifndef FB_ROWS_INV_MINB
+#define FB_ROWS_INV_MINB FB_ROWS_MINB
+#endif
 
 template <int N>
 struct RowGeom {
@@ -414,7 +417,7 @@ __device__ __forceinline__ void run_pk(const KSpace& K, const PkTables& tb, cons
 // and read back in run order (moments) and Stockham order (transform).
 // ---------------------------------------------------------------------------
 template <int N, int SRC>
-__global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_inv(const RowsArgs A) {
+__global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_inv(const RowsArgs A) {
     using G = RowGeom<N>;
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
