@@ -62,6 +62,8 @@ SIGNATURES = {
     "fb_beam_convolve": (_i, [_vp, _vp, _vp, _vp]),
     "fb_halo_counts": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "fb_halo_catalogue": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "fb_fg_cube": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i]),
+    "fb_radiometer_noise": (_i, [_vp, _vp, _vp, _u64, _vp, _i]),
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_c2r_gather": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
@@ -300,6 +302,20 @@ class Plan(object):
         check(self.lib.fb_halo_catalogue(self.h, _ptr(counts), _ptr(uniforms), _ptr(cat_out), int(capacity),
                                          C.byref(nh)))
         return int(nh.value)
+
+    def fg_cube(self, amps, spectral_idx, log2_freq_ratio, out, accumulate=False):
+        """out (+)= amps[x,y] * 2^(idx[x,y] * log2_freq_ratio[z]) (foregrounds.py:152-174); idx: (N,N) map or scalar."""
+        idx = np.ascontiguousarray(np.atleast_1d(spectral_idx), dtype=np.float32)
+        a = np.ascontiguousarray(amps, dtype=np.float32)
+        l2 = np.ascontiguousarray(log2_freq_ratio, dtype=np.float32)
+        check(self.lib.fb_fg_cube(self.h, _ptr(a), _ptr(idx), int(idx.size > 1), _ptr(l2), _ptr(out),
+                                  int(bool(accumulate))))
+
+    def radiometer_noise(self, sigma_z, out, normals=None, seed=0, accumulate=False):
+        """out (+)= sigma_z[z] * n (noise.py:71-75); normals None -> device Philox keyed by seed."""
+        sg = np.ascontiguousarray(sigma_z, dtype=np.float32)
+        check(self.lib.fb_radiometer_noise(self.h, _ptr(sg), _ptr(normals), int(seed), _ptr(out),
+                                           int(bool(accumulate))))
 
     def fft_pass_c2c(self, data, nplanes, axis_pass, sign):
         check(self.lib.fb_fft_pass_c2c(self.h, _ptr(data), int(nplanes), int(axis_pass), int(sign)))

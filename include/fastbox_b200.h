@@ -168,6 +168,19 @@ int fb_halo_counts(fb_plan* plan, const float* delta, const float* nbar, int nba
 int fb_halo_catalogue(fb_plan* plan, const int32_t* counts, const double* uniforms, double* cat_out,
                       uint64_t capacity, uint64_t* nhalo_out);
 
+/* ---- foreground cube: foregrounds.py:152-174 ------------------------------------- */
+/* out[x,y,z] (+)= amps[x,y] * 2^(idx[x,y] * log2_freq_ratio[z]);  log2_freq_ratio[z] = log2(freqs[z]/freq_ref)
+ * (float32 [N], evaluated in float64 by the caller); idx_is_map = 0: spectral_idx points to one float.
+ * accumulate != 0 adds to the cube already in `out` (signal + foregrounds in one pass). */
+int fb_fg_cube(fb_plan* plan, const float* amps, const float* spectral_idx, int idx_is_map,
+               const float* log2_freq_ratio, float* out, int accumulate);
+
+/* ---- radiometer noise: noise.py:55-75 --------------------------------------------- */
+/* out[x,y,z] (+)= sigma_z[z] * n[x,y,z]; normals [N^3] float32 or NULL = Philox4x32-10 N(0,1) keyed by
+ * (seed, cell index) on the device. */
+int fb_radiometer_noise(fb_plan* plan, const float* sigma_z, const float* normals, uint64_t seed, float* out,
+                        int accumulate);
+
 /* ---- building blocks exposed for tests / multi-GPU orchestration ---------------- */
 /* pass = 0: rows (z, contiguous) c2c; 1: columns (y) c2c; sign = -1 fwd / +1 inv;
  * data: [nplanes][N][N] complex64, in place.                                   */

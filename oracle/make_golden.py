@@ -122,10 +122,39 @@ def run_catalogue():
     return out
 
 
+def run_cube():
+    """ForegroundModel (foregrounds.py:48-174) and NoiseModel (noise.py:25-75) of the unmodified reference."""
+    box_m = ref_loader.load("box")
+    fg_m = ref_loader.load("foregrounds")
+    noise_m = ref_loader.load("noise")
+    N = 16
+    box = box_m.CosmoBox(cosmo=box_m.default_cosmo, box_scale=(4e2, 3e2, 2e2), nsamp=N, redshift=0.8,
+                         realise_now=False)
+    fg = fg_m.ForegroundModel(box)
+    out = dict(N=N, scale=np.array([4e2, 3e2, 2e2]), redshift=0.8)
+    np.random.seed(77)
+    out["amps"] = fg.realise_foreground_amp(amp=57., beta=-1.1, monopole=10., smoothing_scale=4.)   # example_endtoend.py:60-62
+    out["amps_nosmooth"] = fg.realise_foreground_amp(amp=57., beta=-1.1, monopole=10.)
+    out["alpha"] = fg.realise_spectral_index(mean_spec_idx=-2.07, std_spec_idx=0.2, smoothing_scale=15.)
+    out["fg_cube_map"] = fg.construct_cube(out["amps"], out["alpha"], freq_ref=130.)
+    out["fg_cube_scalar"] = fg.construct_cube(out["amps"], -2.7, freq_ref=130.)
+    np.random.seed(78)
+    out["noise"] = noise_m.NoiseModel(box).realise_radiometer_noise(Tinst=18., tp=2.5, fov=1., Ndish=64)
+    out["freqs"] = box.freq_array()
+    out["ang_x"] = box.pixel_array()[0]
+    return out
+
+
 def main():
     warnings.simplefilter("ignore")
     dest = os.path.join(ROOT, "tests", "golden")
     os.makedirs(dest, exist_ok=True)
+    if "--cube" in sys.argv or "--all" in sys.argv:
+        path = os.path.join(dest, "fg_noise_cube.npz")
+        np.savez_compressed(path, **run_cube())
+        print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024.))
+        if "--all" not in sys.argv and "--catalogue" not in sys.argv:
+            return
     if "--catalogue" in sys.argv or "--all" in sys.argv:
         path = os.path.join(dest, "halo_catalogue.npz")
         np.savez_compressed(path, **run_catalogue())

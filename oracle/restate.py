@@ -507,6 +507,55 @@ def halo_catalogue_lean(Nhalo, Lx, Ly, Lz, uniforms=None):
     return cat
 
 
+def fg_construct_cube_port(amps, spectral_idx, freqs, freq_ref=130.):
+    """ForegroundModel.construct_cube, foregrounds.py:167-174 (float64 power law per pixel and channel)."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    if isinstance(spectral_idx, float):
+        ffac = ((freqs / freq_ref) ** spectral_idx)[np.newaxis, np.newaxis, :]
+    else:
+        ffac = (freqs / freq_ref)[np.newaxis, np.newaxis, :] ** np.asarray(spectral_idx)[:, :, np.newaxis]
+    return np.asarray(amps)[:, :, np.newaxis] * ffac
+
+
+def radiometer_rms_port(freqs, ang_x, Tinst, tp, fov, Ndish):
+    """NoiseModel.realise_radiometer_noise up to the rms per channel, noise.py:55-69."""
+    freqs = np.asarray(freqs, dtype=np.float64)
+    dnu = np.abs(freqs[1] - freqs[0])
+    tp = tp * 3600.
+    dtheta = ang_x[1] - ang_x[0]
+    t_res = tp * dtheta ** 2. / fov
+    Tsky = 60e3 * (freqs / 300.) ** (-2.5)
+    Tsys = Tinst * 1e3 + Tsky
+    return Tsys / np.sqrt(Ndish * t_res * (dnu * 1e6))
+
+
+def radiometer_noise_port(sigma_rms, normals):
+    """noise.py:72-75: unit white noise times the per-channel rms."""
+    return np.asarray(normals, dtype=np.float64) * np.asarray(sigma_rms)[np.newaxis, np.newaxis, :]
+
+
+def philox_noise_cube(seed, N):
+    """
+    PARITY UNPINNED (the reference draws np.random.normal): the device's counter-based unit normals
+    of the noise cube.  Philox4x32-10 block b = cell index // 4 with counter (b_lo, b_hi, 'NOIS', 0) and
+    key = seed; words (0,1) and (2,3) feed two Box-Muller transforms giving cells 4b .. 4b+3.
+    """
+    n4 = N ** 3 // 4
+    b = np.arange(n4, dtype=np.uint64)
+    ctr = np.zeros((n4, 4), dtype=np.uint32)
+    ctr[:, 0] = (b & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = (b >> np.uint64(32)).astype(np.uint32)
+    ctr[:, 2] = np.uint32(0x4e4f4953)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    x = philox4x32(ctr, key).astype(np.float64)
+    out = np.empty((n4, 4))
+    for j in (0, 2):
+        u1, u2 = (x[:, j] + 0.5) * 2.0 ** -32, (x[:, j + 1] + 0.5) * 2.0 ** -32
+        r = np.sqrt(-2.0 * np.log(u1))
+        out[:, j], out[:, j + 1] = r * np.cos(TWO_PI * u2), r * np.sin(TWO_PI * u2)
+    return out.reshape(N, N, N)
+
+
 # --------------------------------------------------------------------------
 # Counter-based white noise (no reference equivalent: the reference draws
 # from NumPy's global MT19937, box.py:174-175).  Philox4x32-10 keyed by

@@ -164,3 +164,16 @@ def test_halo_catalogue_port_matches_reference_golden(name):
         u = np.random.uniform(0., 1. - 1e-8, cat.size).reshape(cat.shape)       # halos.py:166
         assert np.array_equal(f(counts, *L, uniforms=u), g[name + "_cat_scatter"])
     assert R.halo_catalogue_port(np.zeros((4, 4, 4), int), 1., 1., 1.).shape == (0, 3)
+
+
+def test_fg_and_noise_cube_ports_match_reference_golden():
+    """foregrounds.py:152-174 and noise.py:55-75 restated; bit-identical to the unmodified reference."""
+    g = load_golden("fg_noise_cube")
+    assert np.array_equal(R.fg_construct_cube_port(g["amps"], g["alpha"], g["freqs"]), g["fg_cube_map"])
+    assert np.array_equal(R.fg_construct_cube_port(g["amps"], -2.7, g["freqs"]), g["fg_cube_scalar"])
+    sig = R.radiometer_rms_port(g["freqs"], g["ang_x"], 18., 2.5, 1., 64)
+    np.random.seed(78)
+    n = np.random.normal(0., 1., (16, 16, 16))                                   # noise.py:73
+    assert np.array_equal(R.radiometer_noise_port(sig, n), g["noise"])
+    c = R.philox_noise_cube(5, 16)
+    assert abs(c.mean()) < 0.05 and abs(c.std() - 1) < 0.05

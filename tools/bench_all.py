@@ -93,6 +93,15 @@ def main():
     bias = np.array([1.0], np.float32)
     add("halo counts (Poisson inversion)  [a12]", 16,
         timed(plan, lambda: plan.halo_counts(field, nbar, 0, bias, 0, False, 0.0, u, counts), reps=3))
+    # data-cube steps either side of the beam
+    amps = np.random.default_rng(2).uniform(5., 50., (N, N))
+    alpha = np.random.default_rng(3).normal(-2.5, 0.3, (N, N))
+    l2f = np.log2(np.linspace(700., 1100., N) / 130.)
+    add("foreground cube amps*(nu/nu0)^alpha  [f2]", 4, timed(plan, lambda: plan.fg_cube(amps, alpha, l2f, out), reps=3))
+    add("foreground cube added to a cube  [f2]", 8, timed(plan, lambda: plan.fg_cube(amps, alpha, l2f, out, accumulate=True), reps=3))
+    sig = np.linspace(0.5, 1.5, N)
+    add("radiometer noise, Philox  [f2]", 4, timed(plan, lambda: plan.radiometer_noise(sig, out, None, seed=3), reps=3))
+    add("radiometer noise added to a cube  [f2]", 8, timed(plan, lambda: plan.radiometer_noise(sig, out, None, seed=3, accumulate=True), reps=3))
     # halo catalogue from the counts just drawn: 3 passes over the counts + 24 B per halo
     nh = plan.halo_catalogue(counts)
     cat = plan.alloc(max(nh, 1) * 24)
