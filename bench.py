@@ -120,6 +120,20 @@ def configure_plan(plan, N, L):
     return tables, edges
 
 
+def single_gpu_same_workload(N):
+    """Measured one-GPU rate of the sharded workload (profiles/r1_sizes.json): the denominator for strong
+    scaling.  The N=1 bench line runs BASELINE's single-GPU configuration (1024^3, noise resident in HBM)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_sizes.json")))
+        for r in d["rows"]:
+            if int(r["N"]) == int(N):
+                return {"value": r["philox_Gcells_s"] * 1e3, "unit": "Mcells/s", "ms_per_step": r["philox_ms"],
+                        "source": "profiles/r1_sizes.json (tools/bench_sizes.py, Philox noise, one B200)"}
+    except Exception:
+        pass
+    return None
+
+
 def upload_tables(plan, t):
     plan.set_sqrt_pk(t["lut"], *t["lut_mode"])
     plan.set_filter(t["tperp"], t["tpar"], None)
@@ -425,7 +439,8 @@ def run_multi(args, rank, world, local_rank):
                 "config": {"workload": "%d^3 realise + filter + binned P(k), Philox noise, slab decomposition over "
                                        "%d GPUs, one NCCL all-to-all in %d chunks overlapped with the k-space passes" % (N, world, chunks),
                            "box_Mpc": L,
-                           "l2": "per-GPU working set %.1f GB >> L2" % (12.0 * N ** 3 / world / 1e9)},
+                           "l2": "per-GPU working set %.1f GB >> L2" % (12.0 * N ** 3 / world / 1e9),
+                           "same_workload_on_one_gpu": single_gpu_same_workload(N)},
                 "clocks": clk.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": N ** 3 / t_e2e / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 4 * N ** 3 + world * 3 * 8 * (NBINS + 1), "ms_per_step": t_e2e * 1e3,
