@@ -105,26 +105,37 @@ int pk_clear(fb_plan* p) {
 // the device histogram is replicated FB_PK_COPIES times (CTAs spread their reductions over the
 // copies so that no single L2 address serialises them); fold the copies on the device, then one
 // small pinned D2H copy
-__global__ void k_pk_fold(const unsigned long long* __restrict__ cnt, const double* __restrict__ sums,
-                          unsigned long long* __restrict__ cnt_out, double* __restrict__ sums_out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(32) k_pk_fold(const unsigned long long* __restrict__ cnt,
+                                                const double* __restrict__ sums,
+                                                unsigned long long* __restrict__ cnt_out,
+                                                double* __restrict__ sums_out) {
+    // one warp per bin: lane l folds replicas l, l+32, ..., then a shuffle tree (fixed order: deterministic)
+    const int i = blockIdx.x, lane = threadIdx.x;
     unsigned long long c = 0;
     double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < FB_PK_COPIES; ++k) {
+    for (int k = lane; k < FB_PK_COPIES; k += 32) {
         c += cnt[(size_t)k * (FB_MAX_EDGES + 1) + i];
-        for (int j = 0; j < 4; ++j)
-            s[j] += sums[((size_t)j * FB_PK_COPIES + k) * (FB_MAX_EDGES + 1) + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += sums[((size_t)j * FB_PK_COPIES + k) * (FB_MAX_EDGES + 1) + i];
     }
-    cnt_out[i] = c;
-    for (int j = 0; j < 4; ++j) sums_out[(size_t)j * (FB_MAX_EDGES + 1) + i] = s[j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c += __shfl_down_sync(0xffffffffu, c, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += __shfl_down_sync(0xffffffffu, s[j], d);
+    }
+    if (lane == 0) {
+        cnt_out[i] = c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sums_out[(size_t)j * (FB_MAX_EDGES + 1) + i] = s[j];
+    }
 }
 
 int pk_fetch(fb_plan* p, fb_pk_result* out) {
     const int n = p->nedges + 1;
     unsigned long long* dc = reinterpret_cast<unsigned long long*>(p->pk_fold);
     double* ds = reinterpret_cast<double*>(dc + (FB_MAX_EDGES + 1));
-    k_pk_fold<<<(n + 127) / 128, 128, 0, p->stream>>>(p->h_count, p->h_sums, dc, ds, n);
+    k_pk_fold<<<n, 32, 0, p->stream>>>(p->h_count, p->h_sums, dc, ds);
     FB_LAUNCH_CHECK();
     const size_t bytes = 5 * (size_t)(FB_MAX_EDGES + 1) * 8;
     FB_CUDA(cudaMemcpyAsync(p->pk_host, p->pk_fold, bytes, cudaMemcpyDeviceToHost, p->stream));

@@ -75,7 +75,7 @@ class HaloDistribution(object):
             raise ValueError("Nhalo must have shape (N, N, N)")
         if cnt.size and (cnt.min() < 0 or cnt.max() > np.iinfo(np.int32).max):
             raise ValueError("halo counts must be non-negative 32-bit integers")
-        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+        cnt = plan.upload(np.ascontiguousarray(cnt, dtype=np.int32))     # one upload for the size query and the fill
         nh = plan.halo_catalogue(cnt)
         cat = np.empty((nh, 3), dtype=np.float64)
         if nh == 0:

@@ -94,9 +94,9 @@ def main():
     add("halo counts (Poisson inversion)  [a12]", 16,
         timed(plan, lambda: plan.halo_counts(field, nbar, 0, bias, 0, False, 0.0, u, counts), reps=3))
     # data-cube steps either side of the beam
-    amps = np.random.default_rng(2).uniform(5., 50., (N, N))
-    alpha = np.random.default_rng(3).normal(-2.5, 0.3, (N, N))
-    l2f = np.log2(np.linspace(700., 1100., N) / 130.)
+    amps = np.random.default_rng(2).uniform(5., 50., (N, N)).astype(np.float32)
+    alpha = np.random.default_rng(3).normal(-2.5, 0.3, (N, N)).astype(np.float32)
+    l2f = np.log2(np.linspace(700., 1100., N) / 130.).astype(np.float32)
     add("foreground cube amps*(nu/nu0)^alpha  [f2]", 4, timed(plan, lambda: plan.fg_cube(amps, alpha, l2f, out), reps=3))
     add("foreground cube added to a cube  [f2]", 8, timed(plan, lambda: plan.fg_cube(amps, alpha, l2f, out, accumulate=True), reps=3))
     sig = np.linspace(0.5, 1.5, N)
