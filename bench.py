@@ -324,11 +324,12 @@ def run_single(args):
     cpu = None
     if not args.no_cpu:
         n_cpu = args.cpu_size
-        t_cpu = cpu_port_step(n_cpu, 2000.0 * n_cpu / 1024.0)
+        ts_cpu = [cpu_port_step(n_cpu, 2000.0 * n_cpu / 1024.0, seed=11 + i) for i in range(2)]
+        t_cpu = float(np.mean(ts_cpu))
         cpu = {"value": n_cpu ** 3 / t_cpu / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
-               "sample": "one %d^3 box (%.1f s): NumPy port of fastbox/box.py realise_density + apply_transfer_fn + "
-                         "binned_power_spectrum, float64; numpy.fft is single-threaded as shipped; host has %d cores"
-                         % (n_cpu, t_cpu, os.cpu_count() or 0)}
+               "sample": "two %d^3 boxes (%.1f s in total): NumPy port of fastbox/box.py realise_density + "
+                         "apply_transfer_fn + binned_power_spectrum, float64; numpy.fft is single-threaded as "
+                         "shipped; host has %d cores" % (n_cpu, sum(ts_cpu), os.cpu_count() or 0)}
 
     line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
