@@ -151,6 +151,43 @@ __device__ __forceinline__ PkTables pk_stage_tables(const KSpace& K, double* sm)
     return t;
 }
 
+// Split form of pk_stage_tables for kernels that want the table loads in flight while they issue their
+// own bulk loads: load into registers first, store to shared memory later (before the CTA barrier).
+template <int N>
+struct PkStageRegs {
+    static constexpr int NI = (N / 2 + 255) / 256;       // double2 loads per thread (256 threads)
+    double2 az[NI];
+    double thr;
+};
+template <int N>
+__device__ __forceinline__ void pk_stage_load(const KSpace& K, PkStageRegs<N>& r) {
+    const double2* az2 = reinterpret_cast<const double2*>(K.az);
+#pragma unroll
+    for (int i = 0; i < PkStageRegs<N>::NI; ++i) {
+        const int c = 2 * ((int)threadIdx.x + i * 256);
+        r.az[i] = c < N ? __ldg(az2 + (c >> 1)) : make_double2(0.0, 0.0);
+    }
+    r.thr = (int)threadIdx.x < K.nedges ? __ldg(&K.thr[threadIdx.x]) : 0.0;
+}
+template <int N>
+__device__ __forceinline__ PkTables pk_stage_store(const KSpace& K, const PkStageRegs<N>& r, double* sm) {
+#pragma unroll
+    for (int i = 0; i < PkStageRegs<N>::NI; ++i) {
+        const int c = 2 * ((int)threadIdx.x + i * 256);
+        if (c < N) {
+            double* d = sm + c + (c >> 4);
+            d[0] = r.az[i].x;
+            d[1] = r.az[i].y;
+        }
+    }
+    double* thr = sm + PkSmem<N>::AZ;
+    if ((int)threadIdx.x < K.nedges) thr[threadIdx.x] = r.thr;
+    PkTables t;
+    t.az = sm;
+    t.thr = thr;
+    return t;
+}
+
 struct PkAcc {
     int bin;
     unsigned cnt;
@@ -442,7 +479,8 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
     RowLayout<N> sl{rl * RowLayout<N>::ROW};
     float2 v[P];
     PkTables tb;
-    if (do_pk) tb = pk_stage_tables<N>(A.K, reinterpret_cast<double*>(smem_raw + G::FFT_SMEM));   // visible after the barrier below
+    PkStageRegs<N> stage;                                 // table loads in flight during the prologue
+    if (do_pk) pk_stage_load<N>(A.K, stage);
     // fast path of the prologue (warp-uniform): noise / Philox source, float-bit sqrt(P) table or
     // none, separable filter or none, plain density field
     const bool fast = T > 1 && SRC != SRC_SPEC && SRC != SRC_CUBE && A.kind == FB_KIND_PLAIN && !antiherm &&
@@ -604,6 +642,7 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
         }
     }
     }
+    if (do_pk) tb = pk_stage_store<N>(A.K, stage, reinterpret_cast<double*>(smem_raw + G::FFT_SMEM));
     if (T > 1 || do_pk) __syncthreads();
     // ---- 3. binned moments of |H|^2 (box.py:741-764), run order
     if (do_pk) {
