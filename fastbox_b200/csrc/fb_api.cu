@@ -245,7 +245,7 @@ int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int de
     FB_CUDA(cudaGetDeviceProperties(&prop, device));
     p->sm_count = prop.multiProcessorCount;
     FB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    // twiddles exp(-2 pi i m / NMAX), evaluated in double
+    // twiddles exp(-2 pi i m / n) for every power-of-two n <= FB_NMAX_TW at [n, 2n), evaluated in double
     {
         std::vector<float2> tw(FB_TW_ENTRIES, make_float2(1.f, 0.f));
         for (int n = 1; n <= FB_NMAX_TW; n *= 2)

@@ -52,11 +52,12 @@ struct RowsArgs {
 };
 
 // ---------------------------------------------------------------------------
-// Row kernels.  The k-space prologue / epilogue works in NATURAL order: thread t of a
-// row owns the P consecutive modes c = P*t .. P*t+P-1 (vectorised 16-byte global
-// accesses; the P(k) bin changes at most once or twice along such a run, so moments
-// are accumulated in registers and flushed once per thread).  The FFT itself works in
-// Stockham order (thread t owns t + T*q); one shared-memory transpose connects the two.
+// Row kernels.  Three thread -> mode mappings are used inside one row (see k_rows_inv): quad order
+// for coalesced 16-byte global accesses, run order (P consecutive modes per thread; the P(k) bin
+// changes at most once along such a run, so moments are accumulated in registers and flushed once
+// per thread) and Stockham order (thread t owns t + T*q) for the FFT itself and for evaluating the
+// sqrt(P) amplitudes; shared memory connects them.
+// ---------------------------------------------------------------------------
 // ---------------------------------------------------------------------------
 // bulk read-once data (noise cubes).  ld.global.cs was tried here and measured no better (4.30 vs 4.27 ms).
 template <int P>
