@@ -58,7 +58,6 @@ struct RowsArgs {
 // per thread) and Stockham order (thread t owns t + T*q) for the FFT itself and for evaluating the
 // sqrt(P) amplitudes; shared memory connects them.
 // ---------------------------------------------------------------------------
-// ---------------------------------------------------------------------------
 // bulk read-once data (noise cubes).  ld.global.cs was tried here and measured no better (4.30 vs 4.27 ms).
 template <int P>
 __device__ __forceinline__ void load_run_stream(const float* __restrict__ p, float (&out)[P]) {
