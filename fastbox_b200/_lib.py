@@ -64,6 +64,7 @@ SIGNATURES = {
     "fb_halo_catalogue": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "fb_fg_cube": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i]),
     "fb_radiometer_noise": (_i, [_vp, _vp, _vp, _u64, _vp, _i]),
+    "fb_mean_spectrum_filter": (_i, [_vp, _vp, _vp, _vp]),
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_c2r_gather": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
@@ -316,6 +317,12 @@ class Plan(object):
         sg = np.ascontiguousarray(sigma_z, dtype=np.float32)
         check(self.lib.fb_radiometer_noise(self.h, _ptr(sg), _ptr(normals), int(seed), _ptr(out),
                                            int(bool(accumulate))))
+
+    def mean_spectrum_filter(self, field, out=None):
+        """out = field - per-channel mean over (x, y) (filters.py:35-55); returns the means (float64 [N])."""
+        mean = np.empty(self.N, dtype=np.float64)
+        check(self.lib.fb_mean_spectrum_filter(self.h, _ptr(field), _ptr(out), mean.ctypes.data))
+        return mean
 
     def fft_pass_c2c(self, data, nplanes, axis_pass, sign):
         check(self.lib.fb_fft_pass_c2c(self.h, _ptr(data), int(nplanes), int(axis_pass), int(sign)))

@@ -81,6 +81,51 @@ __global__ void __launch_bounds__(256) k_radiometer_noise(const float* __restric
     }
 }
 
+// ---- mean_spectrum_filter (fastbox/filters.py:35-55): per-channel mean over the N^2 pixels, then
+// subtract.  Sums in float64 (one float64 reduction per channel and CTA); 4 B/cell + 8 B/cell.
+__global__ void __launch_bounds__(256) k_channel_sums(const float* __restrict__ field, int N, size_t nrows,
+                                                       double* __restrict__ sums) {
+    // thread -> channel z = tid (+256 j); a CTA walks a contiguous block of pixel rows
+    const size_t rows_per_cta = (nrows + gridDim.x - 1) / gridDim.x;
+    const size_t r0 = (size_t)blockIdx.x * rows_per_cta;
+    const size_t r1 = r0 + rows_per_cta < nrows ? r0 + rows_per_cta : nrows;
+    for (int z = threadIdx.x; z < N; z += 256) {
+        double acc0 = 0.0, acc1 = 0.0;                    // float64 throughout: a large monopole must not cost digits
+        size_t r = r0;
+        for (; r + 1 < r1; r += 2) {
+            acc0 += (double)__ldg(&field[r * N + z]);
+            acc1 += (double)__ldg(&field[(r + 1) * N + z]);
+        }
+        if (r < r1) acc0 += (double)__ldg(&field[r * N + z]);
+        if (r1 > r0) atomicAdd(&sums[z], acc0 + acc1);
+    }
+}
+
+// the subtraction is done in float64 (the residual of a cube with a large monopole is then the correctly
+// rounded float32 of the exact difference); the kernel stays bound by its 8 B/cell of traffic
+__global__ void __launch_bounds__(256) k_sub_channel(const float* __restrict__ field, const double* __restrict__ mean,
+                                                      int N, size_t n4, float* __restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int per_row = N / 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+        const double2* m2 = reinterpret_cast<const double2*>(mean) + 2 * (q % per_row);
+        const double2 ma = __ldg(m2), mb = __ldg(m2 + 1);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(field) + q);
+        reinterpret_cast<float4*>(out)[q] = make_float4((float)((double)v.x - ma.x), (float)((double)v.y - ma.y),
+                                                        (float)((double)v.z - mb.x), (float)((double)v.w - mb.y));
+    }
+}
+
+__global__ void k_mean_from_sums(const double* __restrict__ sums, double inv_n, int N, double* __restrict__ mean64,
+                                 float* __restrict__ mean32) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z < N) {
+        const double m = sums[z] * inv_n;
+        mean64[z] = m;
+        mean32[z] = (float)m;
+    }
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -148,6 +193,40 @@ int fb_radiometer_noise(fb_plan* p, const float* sigma_z, const float* normals, 
     else
         k_radiometer_noise<false><<<grid, 256, 0, p->stream>>>(d_sigma, (const float*)dn, seed, N, n4, (float*)dout);
     FB_LAUNCH_CHECK();
+    if (stage_out_end(p, 2, out, n3 * sizeof(float))) return -2;
+    return 0;
+}
+
+int fb_mean_spectrum_filter(fb_plan* p, const float* field, float* out, double* mean_out) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const int N = p->N;
+    FB_CHECK(field, "fb_mean_spectrum_filter: NULL field");
+    const size_t n2 = (size_t)N * N, n3 = n2 * N;
+    const void* din = nullptr;
+    void* dout = nullptr;
+    if (stage_in(p, 0, field, n3 * sizeof(float), &din)) return -2;
+    if (stage_out_begin(p, 2, out, n3 * sizeof(float), &dout)) return -2;
+    // aux: sums [N] f64, mean [N] f64, mean [N] f32
+    if (ensure_aux(p, (size_t)N * (2 * sizeof(double) + sizeof(float)))) return -2;
+    double* d_sums = (double*)p->aux;
+    double* d_mean64 = d_sums + N;
+    float* d_mean32 = (float*)(d_mean64 + N);
+    FB_CUDA(cudaMemsetAsync(d_sums, 0, (size_t)N * sizeof(double), p->stream));
+    const unsigned grid = (unsigned)((size_t)p->sm_count * 8 < n2 ? (size_t)p->sm_count * 8 : n2);
+    k_channel_sums<<<grid, 256, 0, p->stream>>>((const float*)din, N, n2, d_sums);
+    FB_LAUNCH_CHECK();
+    k_mean_from_sums<<<(N + 255) / 256, 256, 0, p->stream>>>(d_sums, 1.0 / (double)n2, N, d_mean64, d_mean32);
+    FB_LAUNCH_CHECK();
+    if (dout) {
+        const size_t n4 = n3 / 4, want = (n4 + 255) / 256, cap = (size_t)p->sm_count * 32;
+        k_sub_channel<<<(unsigned)(want < cap ? want : cap), 256, 0, p->stream>>>((const float*)din, d_mean64, N, n4,
+                                                                                (float*)dout);
+        FB_LAUNCH_CHECK();
+    }
+    if (mean_out) {
+        FB_CUDA(cudaMemcpyAsync(mean_out, d_mean64, (size_t)N * sizeof(double), cudaMemcpyDefault, p->stream));
+        FB_CUDA(cudaStreamSynchronize(p->stream));
+    }
     if (stage_out_end(p, 2, out, n3 * sizeof(float))) return -2;
     return 0;
 }

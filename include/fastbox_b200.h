@@ -181,6 +181,11 @@ int fb_fg_cube(fb_plan* plan, const float* amps, const float* spectral_idx, int 
 int fb_radiometer_noise(fb_plan* plan, const float* sigma_z, const float* normals, uint64_t seed, float* out,
                         int accumulate);
 
+/* ---- mean_spectrum_filter: filters.py:35-55 ---------------------------------------- */
+/* out[x,y,z] = field[x,y,z] - mean_xy(field[:,:,z]); mean_out [N] float64 (nullable); out nullable
+ * (mean only).  The per-channel sums are accumulated in float64. */
+int fb_mean_spectrum_filter(fb_plan* plan, const float* field, float* out, double* mean_out);
+
 /* ---- building blocks exposed for tests / multi-GPU orchestration ---------------- */
 /* pass = 0: rows (z, contiguous) c2c; 1: columns (y) c2c; sign = -1 fwd / +1 inv;
  * data: [nplanes][N][N] complex64, in place.                                   */

@@ -142,6 +142,9 @@ def run_cube():
     out["noise"] = noise_m.NoiseModel(box).realise_radiometer_noise(Tinst=18., tp=2.5, fov=1., Ndish=64)
     out["freqs"] = box.freq_array()
     out["ang_x"] = box.pixel_array()[0]
+    filters_m = ref_loader.load_pkg("filters")
+    out["data_cube"] = out["fg_cube_map"] + out["noise"]
+    out["mean_filtered"] = filters_m.mean_spectrum_filter(out["data_cube"])      # filters.py:35-55
     return out
 
 

@@ -59,3 +59,26 @@ def load(name):
     spec.loader.exec_module(mod)
     _cache[name] = mod
     return mod
+
+
+def load_pkg(name):
+    """
+    Reference module that uses package-relative imports (``filters.py`` imports ``.foregrounds``):
+    imported as ``fastbox_refpkg.<name>`` from a synthetic package whose path is the reference's
+    ``fastbox/`` directory, so the reference's own ``__init__`` (which pulls in absent dependencies)
+    is not executed and the source files stay unmodified.
+    """
+    key = "pkg:" + name
+    if key in _cache:
+        return _cache[key]
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    _install_stubs()
+    if "fastbox_refpkg" not in sys.modules:
+        pkg = types.ModuleType("fastbox_refpkg")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "fastbox")]
+        sys.modules["fastbox_refpkg"] = pkg
+    mod = importlib.import_module("fastbox_refpkg." + name)
+    _cache[key] = mod
+    return mod
+

@@ -517,6 +517,13 @@ def fg_construct_cube_port(amps, spectral_idx, freqs, freq_ref=130.):
     return np.asarray(amps)[:, :, np.newaxis] * ffac
 
 
+def mean_spectrum_filter_port(field):
+    """filters.mean_spectrum_filter, filters.py:49-55: subtract the pixel-averaged spectrum."""
+    d = np.asarray(field).reshape((-1, field.shape[-1]))
+    d_mean = np.mean(d, axis=0)[np.newaxis, :]
+    return (d - d_mean).reshape(field.shape)
+
+
 def radiometer_rms_port(freqs, ang_x, Tinst, tp, fov, Ndish):
     """NoiseModel.realise_radiometer_noise up to the rms per channel, noise.py:55-69."""
     freqs = np.asarray(freqs, dtype=np.float64)

@@ -87,3 +87,25 @@ def test_cube_kernels_vs_oracle(gpu, N):
     # carry the absolute error of __logf near 1, hence the looser bound on the maximum
     assert rel_l2(out, ref) < TOL and np.max(np.abs(out - ref)) < 1e-3 * sig.max()
     plan.close()
+
+
+def test_mean_spectrum_filter(gpu):
+    """filters.mean_spectrum_filter (filters.py:35-55): golden of the unmodified reference, then a cube with a
+    large monopole (the per-channel sums are float64, so the residual keeps its digits)."""
+    g = load_golden("fg_noise_cube")
+    out, mean = fb.filters.mean_spectrum_filter(g["data_cube"], return_mean=True)
+    assert out.dtype == np.float64 and out.shape == g["mean_filtered"].shape
+    ref_mean = g["data_cube"].reshape(-1, out.shape[-1]).mean(axis=0)
+    assert np.allclose(mean, ref_mean, rtol=1e-6, atol=0)
+    # the cube is float32 on the device: tolerance relative to the cube, not to the (much smaller) residual
+    scale = np.sqrt(np.mean(g["data_cube"] ** 2))
+    assert np.sqrt(np.mean((out - g["mean_filtered"]) ** 2)) < TOL * scale
+    rng = np.random.default_rng(3)
+    N = 64
+    cube = (1e4 * np.linspace(1.0, 2.0, N)[None, None, :] + rng.standard_normal((N, N, N))).astype(np.float32)
+    out = fb.filters.mean_spectrum_filter(cube)
+    ref = R.mean_spectrum_filter_port(cube.astype(np.float64))
+    assert np.max(np.abs(out - ref)) < 1e-6                # float64 subtraction: only the final float32 rounding of O(1) values
+    assert abs(out.mean()) < 1e-7
+    with pytest.raises(ValueError):
+        fb.filters.mean_spectrum_filter(np.zeros((4, 4, 8)))

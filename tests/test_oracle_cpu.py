@@ -177,3 +177,9 @@ def test_fg_and_noise_cube_ports_match_reference_golden():
     assert np.array_equal(R.radiometer_noise_port(sig, n), g["noise"])
     c = R.philox_noise_cube(5, 16)
     assert abs(c.mean()) < 0.05 and abs(c.std() - 1) < 0.05
+
+
+def test_mean_spectrum_filter_port_matches_reference_golden():
+    """filters.py:35-55 restated; bit-identical to the unmodified reference."""
+    g = load_golden("fg_noise_cube")
+    assert np.array_equal(R.mean_spectrum_filter_port(g["data_cube"]), g["mean_filtered"])
