@@ -65,6 +65,8 @@ SIGNATURES = {
     "fb_fg_cube": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i]),
     "fb_radiometer_noise": (_i, [_vp, _vp, _vp, _u64, _vp, _i]),
     "fb_mean_spectrum_filter": (_i, [_vp, _vp, _vp, _vp]),
+    "fb_pca_covariance": (_i, [_vp, _vp, _vp, _vp]),
+    "fb_pca_project": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_c2r_gather": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
@@ -323,6 +325,20 @@ class Plan(object):
         mean = np.empty(self.N, dtype=np.float64)
         check(self.lib.fb_mean_spectrum_filter(self.h, _ptr(field), _ptr(out), mean.ctypes.data))
         return mean
+
+    def pca_covariance(self, cube):
+        """(mean [N], cov [N,N]) of a DEVICE float64 cube [N*N pixels][N channels] (filters.py:142,158-159)."""
+        mean = np.empty(self.N, dtype=np.float64)
+        cov = np.empty((self.N, self.N), dtype=np.float64)
+        check(self.lib.fb_pca_covariance(self.h, _ptr(cube), mean.ctypes.data, cov.ctypes.data))
+        return mean, cov
+
+    def pca_project(self, cube, mean, U, cleaned, amps=None):
+        """cleaned = cube - (U U^T (cube - mean) + mean) on the device (filters.py:173-178); U (N, nmodes)."""
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        check(self.lib.fb_pca_project(self.h, _ptr(cube), mean.ctypes.data, U.ctypes.data, int(U.shape[1]),
+                                      _ptr(cleaned), _ptr(amps)))
 
     def fft_pass_c2c(self, data, nplanes, axis_pass, sign):
         check(self.lib.fb_fft_pass_c2c(self.h, _ptr(data), int(nplanes), int(axis_pass), int(sign)))

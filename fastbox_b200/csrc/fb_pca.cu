@@ -1,0 +1,227 @@
+// fb_pca.cu -- the device steps of filters.pca_filter (fastbox/filters.py:93-183), in FLOAT64:
+//     d_mean = mean over pixels per channel                      (filters.py:142)
+//     cov    = np.cov(d - d_mean)            [Nf x Nf]           (filters.py:158-159)
+//     (eigen-decomposition of cov: host, Nf x Nf)                (filters.py:162-170)
+//     fg_amps = U^T (d - d_mean), cleaned = field - (U fg_amps + d_mean)   (filters.py:173-178)
+// Why float64: with foregrounds 1e4-1e5 x the signal a float32 cube perturbs the data by
+// ~1e-2 of the signal, and an error eps in the covariance leaks a foreground mode as eps*lambda_1/sqrt(lambda_i).
+// The cube is [pixel][channel] (channel contiguous), exactly field.reshape(-1, Nf) of the reference.
+//
+// k_pca_cov: tall-skinny X^T X.  A CTA owns one 64 x 64 tile of the upper triangle and one slice of the
+// pixels; 256 threads hold 4 x 4 float64 accumulators each; panels of 16 pixels x 64 channels go through
+// shared memory (mean subtracted on the way in); partial tiles are added to the global matrix with float64
+// reductions.  FP64-FMA bound: 2 * Nf^2/2 * Npix flops.
+// k_pca_project: one CTA per pixel row: nmodes block reductions for the amplitudes, then the residual.
+#include "fb_launch.h"
+
+namespace fb {
+
+constexpr int PCA_TILE = 64, PCA_KT = 16;
+
+__global__ void __launch_bounds__(256) k_pca_sums(const double* __restrict__ x, int nf, size_t npix,
+                                                   double* __restrict__ sums) {
+    const size_t rows_per_cta = (npix + gridDim.x - 1) / gridDim.x;
+    const size_t r0 = (size_t)blockIdx.x * rows_per_cta;
+    const size_t r1 = r0 + rows_per_cta < npix ? r0 + rows_per_cta : npix;
+    for (int z = threadIdx.x; z < nf; z += 256) {
+        double a0 = 0.0, a1 = 0.0;
+        size_t r = r0;
+        for (; r + 1 < r1; r += 2) {
+            a0 += __ldg(&x[r * nf + z]);
+            a1 += __ldg(&x[(r + 1) * nf + z]);
+        }
+        if (r < r1) a0 += __ldg(&x[r * nf + z]);
+        if (r1 > r0) atomicAdd(&sums[z], a0 + a1);
+    }
+}
+
+__global__ void k_pca_scale(double* __restrict__ v, int n, double s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] *= s;
+}
+
+// grid = (upper-triangle tiles, pixel slices)
+__global__ void __launch_bounds__(256) k_pca_cov(const double* __restrict__ x, const double* __restrict__ mean, int nf,
+                                                  size_t npix, int ntile, double* __restrict__ cov) {
+    __shared__ double sa[PCA_KT][PCA_TILE + 2], sb[PCA_KT][PCA_TILE + 2];
+    // tile index -> (ti <= tj)
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= ntile - ti) {
+        rem -= ntile - ti;
+        ++ti;
+    }
+    const int tj = ti + rem;
+    const int f0 = ti * PCA_TILE, g0 = tj * PCA_TILE;
+    const size_t per_slice = (npix + gridDim.y - 1) / gridDim.y;
+    const size_t p0 = (size_t)blockIdx.y * per_slice;
+    const size_t p1 = p0 + per_slice < npix ? p0 + per_slice : npix;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;           // 16 x 16 threads, 4 x 4 outputs each
+    const int lc = threadIdx.x % PCA_TILE, lr = threadIdx.x / PCA_TILE;   // loader: 64 channels x 4 pixel rows
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const double ma = (f0 + lc) < nf ? __ldg(&mean[f0 + lc]) : 0.0;
+    const double mb = (g0 + lc) < nf ? __ldg(&mean[g0 + lc]) : 0.0;
+    for (size_t pb = p0; pb < p1; pb += PCA_KT) {
+#pragma unroll
+        for (int k = lr; k < PCA_KT; k += 4) {
+            const size_t p = pb + k;
+            double va = 0.0, vb = 0.0;
+            if (p < p1) {
+                if (f0 + lc < nf) va = __ldg(&x[p * nf + f0 + lc]) - ma;
+                if (g0 + lc < nf) vb = __ldg(&x[p * nf + g0 + lc]) - mb;
+            }
+            sa[k][lc] = va;
+            sb[k][lc] = vb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PCA_KT; ++k) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = sa[k][ty + 16 * i];
+                b[i] = sb[k][tx + 16 * i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = f0 + ty + 16 * i, g = g0 + tx + 16 * j;
+            if (f < nf && g < nf) atomicAdd(&cov[(size_t)f * nf + g], acc[i][j]);
+        }
+}
+
+// mirror the upper-triangle tiles into the lower triangle and apply the 1/(npix-1) of np.cov
+__global__ void k_pca_cov_finish(double* __restrict__ cov, int nf, double norm) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (g >= nf) return;
+    if (f <= g) {                                        // element-wise: the result is exactly symmetric even though
+        const double v = cov[(size_t)f * nf + g] * norm;  // the slices' reductions arrive in any order
+        cov[(size_t)f * nf + g] = v;
+        if (f < g) cov[(size_t)g * nf + f] = v;
+    }
+}
+
+// one CTA (256 threads) per pixel row: amplitudes by block reduction, then the residual
+template <int MAXM>
+__global__ void __launch_bounds__(256) k_pca_project(const double* __restrict__ x, const double* __restrict__ mean,
+                                                      const double* __restrict__ U, int nf, int nmodes, size_t npix,
+                                                      double* __restrict__ cleaned, double* __restrict__ amps) {
+    __shared__ double red[8][MAXM];
+    __shared__ double a_sh[MAXM];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (size_t p = blockIdx.x; p < npix; p += gridDim.x) {
+        double part[MAXM];
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) part[m] = 0.0;
+        for (int f = tid; f < nf; f += 256) {
+            const double d = __ldg(&x[p * nf + f]) - __ldg(&mean[f]);
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m)
+                if (m < nmodes) part[m] = fma(__ldg(&U[(size_t)f * nmodes + m]), d, part[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < nmodes) {
+                double v = part[m];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp][m] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < nmodes) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += red[w][tid];
+            a_sh[tid] = v;
+            if (amps) amps[(size_t)tid * npix + p] = v;              // (Nmodes, Npix), filters.py:173
+        }
+        __syncthreads();
+        for (int f = tid; f < nf; f += 256) {
+            double fg = 0.0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m)
+                if (m < nmodes) fg = fma(__ldg(&U[(size_t)f * nmodes + m]), a_sh[m], fg);
+            // cleaned = field - (U amps + mean), filters.py:176-178
+            cleaned[p * nf + f] = __ldg(&x[p * nf + f]) - (fg + __ldg(&mean[f]));
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* cov_out) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const int nf = p->N;
+    const size_t npix = (size_t)nf * nf;
+    FB_CHECK(cube && cov_out, "fb_pca_covariance: NULL buffer");
+    FB_CHECK(is_device_ptr(cube), "fb_pca_covariance: the float64 cube must be device memory");
+    if (ensure_aux(p, ((size_t)nf * nf + nf) * sizeof(double))) return -2;
+    double* d_cov = (double*)p->aux;
+    double* d_mean = d_cov + (size_t)nf * nf;
+    {   // np.cov centres every channel on its own mean, whatever was subtracted before (filters.py:158-159)
+        FB_CUDA(cudaMemsetAsync(d_mean, 0, nf * sizeof(double), p->stream));
+        const unsigned grid = (unsigned)((size_t)p->sm_count * 8 < npix ? (size_t)p->sm_count * 8 : npix);
+        k_pca_sums<<<grid, 256, 0, p->stream>>>(cube, nf, npix, d_mean);
+        FB_LAUNCH_CHECK();
+        k_pca_scale<<<(nf + 255) / 256, 256, 0, p->stream>>>(d_mean, nf, 1.0 / (double)npix);
+        FB_LAUNCH_CHECK();
+    }
+    FB_CUDA(cudaMemsetAsync(d_cov, 0, (size_t)nf * nf * sizeof(double), p->stream));
+    const int ntile = (nf + PCA_TILE - 1) / PCA_TILE;
+    const int ntri = ntile * (ntile + 1) / 2;
+    int slices = (p->sm_count * 4 + ntri - 1) / ntri;
+    const size_t max_slices = (npix + PCA_KT - 1) / PCA_KT;
+    if ((size_t)slices > max_slices) slices = (int)max_slices;
+    if (slices < 1) slices = 1;
+    k_pca_cov<<<dim3(ntri, slices), 256, 0, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
+    FB_LAUNCH_CHECK();
+    k_pca_cov_finish<<<dim3((nf + 255) / 256, nf), 256, 0, p->stream>>>(d_cov, nf, 1.0 / (double)(npix - 1));
+    FB_LAUNCH_CHECK();
+    FB_CUDA(cudaMemcpyAsync(cov_out, d_cov, (size_t)nf * nf * sizeof(double), cudaMemcpyDefault, p->stream));
+    if (mean_out) FB_CUDA(cudaMemcpyAsync(mean_out, d_mean, nf * sizeof(double), cudaMemcpyDefault, p->stream));
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int fb_pca_project(fb_plan* p, const double* cube, const double* mean, const double* U, int nmodes, double* cleaned,
+                   double* amps) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const int nf = p->N;
+    const size_t npix = (size_t)nf * nf;
+    FB_CHECK(cube && mean && U && cleaned, "fb_pca_project: NULL buffer");
+    FB_CHECK(is_device_ptr(cube) && is_device_ptr(cleaned) && (!amps || is_device_ptr(amps)),
+             "fb_pca_project: cube / cleaned / amps must be device memory");
+    FB_CHECK(nmodes >= 1 && nmodes <= 32, "fb_pca_project: nmodes=%d out of range [1,32]", nmodes);
+    if (ensure_aux(p, ((size_t)nf * nmodes + nf) * sizeof(double))) return -2;
+    double* d_U = (double*)p->aux;
+    double* d_mean = d_U + (size_t)nf * nmodes;
+    FB_CUDA(cudaMemcpyAsync(d_U, U, (size_t)nf * nmodes * sizeof(double), cudaMemcpyDefault, p->stream));
+    FB_CUDA(cudaMemcpyAsync(d_mean, mean, nf * sizeof(double), cudaMemcpyDefault, p->stream));
+    const unsigned grid = (unsigned)((size_t)p->sm_count * 8 < npix ? (size_t)p->sm_count * 8 : npix);
+    if (nmodes <= 8)
+        k_pca_project<8><<<grid, 256, 0, p->stream>>>(cube, d_mean, d_U, nf, nmodes, npix, cleaned, amps);
+    else
+        k_pca_project<32><<<grid, 256, 0, p->stream>>>(cube, d_mean, d_U, nf, nmodes, npix, cleaned, amps);
+    FB_LAUNCH_CHECK();
+    FB_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+}  // extern "C"

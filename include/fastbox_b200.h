@@ -186,6 +186,17 @@ int fb_radiometer_noise(fb_plan* plan, const float* sigma_z, const float* normal
  * (mean only).  The per-channel sums are accumulated in float64. */
 int fb_mean_spectrum_filter(fb_plan* plan, const float* field, float* out, double* mean_out);
 
+/* ---- PCA foreground filter, device steps in float64: filters.py:93-183 ------------ */
+/* cube: DEVICE float64 [N*N pixels][N channels] (= field.reshape(-1, Nf) of the reference).
+ * fb_pca_covariance: mean_out[N] = per-channel mean (filters.py:142), cov_out[N*N] = np.cov of the
+ * channels over the pixels (filters.py:158-159, normalised by Npix-1); host or device outputs.
+ * fb_pca_project: amps[nmodes][Npix] = U^T (cube - mean) (nullable, device), cleaned = cube - (U amps + mean)
+ * (filters.py:173-178); U [N][nmodes] float64 row-major, 1 <= nmodes <= 32; cleaned: device.
+ * The eigen-decomposition of cov between the two calls is the caller's (N x N, host). */
+int fb_pca_covariance(fb_plan* plan, const double* cube, double* mean_out, double* cov_out);
+int fb_pca_project(fb_plan* plan, const double* cube, const double* mean, const double* U, int nmodes,
+                   double* cleaned, double* amps);
+
 /* ---- building blocks exposed for tests / multi-GPU orchestration ---------------- */
 /* pass = 0: rows (z, contiguous) c2c; 1: columns (y) c2c; sign = -1 fwd / +1 inv;
  * data: [nplanes][N][N] complex64, in place.                                   */

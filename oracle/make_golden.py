@@ -145,6 +145,18 @@ def run_cube():
     filters_m = ref_loader.load_pkg("filters")
     out["data_cube"] = out["fg_cube_map"] + out["noise"]
     out["mean_filtered"] = filters_m.mean_spectrum_filter(out["data_cube"])      # filters.py:35-55
+    # PCA cleaning (filters.py:93-183) of foregrounds + noise + a small "signal" (example_endtoend.py:101-105)
+    np.random.seed(79)
+    sig = 0.1 * np.random.normal(0., 1., out["data_cube"].shape)
+    out["pca_cube"] = out["data_cube"] + sig
+    for nm in (2, 4):
+        out["pca_clean%d" % nm] = np.real(filters_m.pca_filter(out["pca_cube"], nmodes=nm))
+    c, U, a = filters_m.pca_filter(out["pca_cube"], nmodes=3, return_filter=True)
+    out["pca_clean3"], out["pca_U3"], out["pca_amps3"] = np.real(c), np.real(U), np.real(a)
+    out["pca_clean3_pl"] = np.real(filters_m.pca_filter(out["pca_cube"], nmodes=3, fit_powerlaw=True))
+    # foreground-dominated cube: foregrounds ~3e3 x the signal
+    out["pca_cube_fg"] = 1e3 * out["fg_cube_map"] + out["noise"] + sig
+    out["pca_fg_clean3"] = np.real(filters_m.pca_filter(out["pca_cube_fg"], nmodes=3))
     return out
 
 

@@ -524,6 +524,34 @@ def mean_spectrum_filter_port(field):
     return (d - d_mean).reshape(field.shape)
 
 
+def pca_filter_port(field, nmodes, fit_powerlaw=False, return_filter=False):
+    """
+    filters.pca_filter, filters.py:138-183, step by step: mean spectrum (optionally its power-law fit,
+    filters.py:146-155), np.cov of the mean-subtracted channels, np.linalg.eig, modes sorted by
+    eigenvalue, amplitudes U^T x per line of sight, foreground model U a + mean subtracted.
+    """
+    d = field.reshape((-1, field.shape[-1])).T
+    d_mean = np.mean(d, axis=-1)[:, np.newaxis]
+    if fit_powerlaw:
+        from scipy.optimize import curve_fit
+        freqs = np.linspace(1., 10., d.shape[0])
+
+        def fn(nu, amp, beta):
+            return amp * (nu / nu[0]) ** beta
+        pfit, _ = curve_fit(fn, freqs, d_mean.flatten(), p0=[d_mean[0][0], -2.7])
+        d_mean = fn(freqs, pfit[0], pfit[1])[:, np.newaxis]
+    x = d - d_mean
+    cov = np.cov(x)
+    eigvals, eigvecs = np.linalg.eig(cov)
+    idxs = np.argsort(eigvals)[::-1]
+    eigvecs = eigvecs[:, idxs]
+    U_fg = eigvecs[:, :nmodes]
+    fg_amps = np.dot(U_fg.T, x)
+    fg_field = (np.dot(U_fg, fg_amps) + d_mean).T.reshape(field.shape)
+    cleaned = field - fg_field
+    return (cleaned, U_fg, fg_amps) if return_filter else cleaned
+
+
 def radiometer_rms_port(freqs, ang_x, Tinst, tp, fov, Ndish):
     """NoiseModel.realise_radiometer_noise up to the rms per channel, noise.py:55-69."""
     freqs = np.asarray(freqs, dtype=np.float64)

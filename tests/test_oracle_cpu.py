@@ -183,3 +183,18 @@ def test_mean_spectrum_filter_port_matches_reference_golden():
     """filters.py:35-55 restated; bit-identical to the unmodified reference."""
     g = load_golden("fg_noise_cube")
     assert np.array_equal(R.mean_spectrum_filter_port(g["data_cube"]), g["mean_filtered"])
+
+
+def test_pca_filter_port_matches_reference_golden():
+    """filters.py:93-183 restated; bit-identical to the unmodified reference (same LAPACK underneath)."""
+    import warnings
+    g = load_golden("fg_noise_cube")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for nm in (2, 4):
+            assert np.array_equal(R.pca_filter_port(g["pca_cube"], nm), g["pca_clean%d" % nm])
+        c, U, a = R.pca_filter_port(g["pca_cube"], 3, return_filter=True)
+        assert np.array_equal(c, g["pca_clean3"]) and np.array_equal(np.real(U), g["pca_U3"])
+        assert np.array_equal(np.real(a), g["pca_amps3"])
+        assert np.array_equal(np.real(R.pca_filter_port(g["pca_cube"], 3, fit_powerlaw=True)), g["pca_clean3_pl"])
+        assert np.array_equal(R.pca_filter_port(g["pca_cube_fg"], 3), g["pca_fg_clean3"])
