@@ -102,6 +102,20 @@ def main():
     sig = np.linspace(0.5, 1.5, N)
     add("radiometer noise, Philox  [f2]", 4, timed(plan, lambda: plan.radiometer_noise(sig, out, None, seed=3), reps=3))
     add("radiometer noise added to a cube  [f2]", 8, timed(plan, lambda: plan.radiometer_noise(sig, out, None, seed=3, accumulate=True), reps=3))
+    # PCA foreground filter, float64 device steps
+    if N <= 1024:
+        rng = np.random.default_rng(4)
+        cube64 = plan.alloc(n3 * 8)
+        clean64 = plan.alloc(n3 * 8)
+        plan.lib.fb_convert_f32_to_f64(plan.h, _lib._ptr(field), _lib._ptr(cube64), n3)
+        ms = timed(plan, lambda: plan.pca_covariance(cube64), reps=2)
+        flops = 2.0 * (N * (N + 64) / 2.0) * N * N                 # upper-triangle tiles incl. the diagonal ones
+        add("PCA covariance, float64, %.1f TFLOP/s FP64  [f3]" % (flops / (ms * 1e-3) / 1e12), 8, ms)
+        mean, cov = plan.pca_covariance(cube64)
+        w, v = np.linalg.eigh(cov)
+        U = np.ascontiguousarray(v[:, ::-1][:, :4])
+        add("PCA projection (4 modes), float64  [f3]", 16, timed(plan, lambda: plan.pca_project(cube64, mean, U, clean64), reps=2))
+        del cube64, clean64
     # halo catalogue from the counts just drawn: 3 passes over the counts + 24 B per halo
     nh = plan.halo_catalogue(counts)
     cat = plan.alloc(max(nh, 1) * 24)
