@@ -176,6 +176,34 @@ def test_no_cpu_fallback_without_gpu():
     box = fb.CosmoBox(cosmo=fb.default_cosmo, box_scale=1e2, nsamp=16, realise_now=False)
     with pytest.raises(_lib.FastBoxError):
         box.realise_density()
+    # the rows added from SURVEY 8(f) have no CPU path either
+    cube = np.zeros((16, 16, 16))
+    with pytest.raises(_lib.FastBoxError):
+        fb.filters.mean_spectrum_filter(cube)
+    with pytest.raises(_lib.FastBoxError):
+        fb.filters.pca_filter(cube, nmodes=2)
+    with pytest.raises(_lib.FastBoxError):
+        fb.halos.HaloDistribution(box, (1e12, 1e15), 10).realise_halo_catalogue(np.ones((16, 16, 16), int))
+    with pytest.raises(_lib.FastBoxError):
+        fb.foregrounds.ForegroundModel(box).construct_cube(np.ones((16, 16)), -2.7)
+    with pytest.raises(_lib.FastBoxError):
+        fb.noise.NoiseModel(box).realise_radiometer_noise(18., 2., 1., 64, seed=1)
+
+
+def test_host_maps_of_the_foreground_model_need_no_gpu():
+    """The N^2 maps are host work with the reference's own NumPy / SciPy calls (foregrounds.py:48-149):
+    bit-identical to the unmodified reference's golden output under the same seed."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fg_noise_cube.npz"))
+    box = fb.CosmoBox(cosmo=fb.default_cosmo, box_scale=tuple(g["scale"]), nsamp=int(g["N"]),
+                      redshift=float(g["redshift"]), realise_now=False)
+    fg = fb.foregrounds.ForegroundModel(box)
+    np.random.seed(77)
+    assert np.array_equal(fg.realise_foreground_amp(amp=57., beta=-1.1, monopole=10., smoothing_scale=4.), g["amps"])
+    assert np.array_equal(fg.realise_foreground_amp(amp=57., beta=-1.1, monopole=10.), g["amps_nosmooth"])
+    assert np.array_equal(fg.realise_spectral_index(mean_spec_idx=-2.07, std_spec_idx=0.2, smoothing_scale=15.),
+                          g["alpha"])
+    sig = fb.noise.NoiseModel(box).radiometer_rms(18., 2.5, 1., 64)
+    assert sig.shape == (int(g["N"]),) and np.all(sig > 0)
 
 
 def test_product_never_imports_oracle():
