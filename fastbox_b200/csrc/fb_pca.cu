@@ -11,7 +11,8 @@
 // pixels; 256 threads hold 4 x 4 float64 accumulators each; panels of 16 pixels x 64 channels go through
 // shared memory (mean subtracted on the way in); partial tiles are added to the global matrix with float64
 // reductions.  FP64-FMA bound: 2 * Nf^2/2 * Npix flops.
-// k_pca_project: one CTA per pixel row: nmodes block reductions for the amplitudes, then the residual.
+// k_pca_project_warp: one warp per line of sight, row in registers, operator in shared memory (nmodes <= 8);
+// k_pca_project: general fallback, one CTA per line of sight with block reductions.
 #include "fb_launch.h"
 
 namespace fb {
@@ -160,6 +161,66 @@ __global__ void __launch_bounds__(256) k_pca_project(const double* __restrict__ 
     }
 }
 
+// Streaming variant for nmodes <= 8 and nf >= 32: one WARP per line of sight.  The row stays in
+// registers (nf/32 float64 per lane) between the amplitude sums and the residual, the amplitudes need only
+// warp shuffles, and the filter operator sits in shared memory as [mode][channel] (conflict-free).
+template <int NF>
+__global__ void __launch_bounds__(256) k_pca_project_warp(const double* __restrict__ x, const double* __restrict__ mean,
+                                                           const double* __restrict__ U, int nmodes, size_t npix,
+                                                           double* __restrict__ cleaned, double* __restrict__ amps) {
+    constexpr int E = NF / 32;
+    extern __shared__ __align__(16) unsigned char pca_smem[];
+    double* us = reinterpret_cast<double*>(pca_smem);            // [nmodes][NF]
+    double* ms = us + (size_t)nmodes * NF;                       // [NF]
+    for (int i = threadIdx.x; i < nmodes * NF; i += blockDim.x) {
+        const int m = i / NF, f = i - m * NF;
+        us[i] = __ldg(&U[(size_t)f * nmodes + m]);
+    }
+    for (int f = threadIdx.x; f < NF; f += blockDim.x) ms[f] = __ldg(&mean[f]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t p = warp0; p < npix; p += nwarps) {
+        double v[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = __ldg(&x[p * NF + lane + 32 * i]);
+        double a[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            a[m] = 0.0;
+            if (m < nmodes) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < E; ++i) s = fma(us[m * NF + lane + 32 * i], v[i] - ms[lane + 32 * i], s);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                a[m] = s;
+                if (amps && lane == 0) amps[(size_t)m * npix + p] = s;      // (Nmodes, Npix), filters.py:173
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            double fg = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (m < nmodes) fg = fma(us[m * NF + lane + 32 * i], a[m], fg);
+            cleaned[p * NF + lane + 32 * i] = v[i] - (fg + ms[lane + 32 * i]);   // filters.py:176-178
+        }
+    }
+}
+
+template <int NF>
+static int launch_project_warp(fb_plan* p, const double* cube, const double* d_mean, const double* d_U, int nmodes,
+                               size_t npix, double* cleaned, double* amps) {
+    auto kern = k_pca_project_warp<NF>;
+    const size_t smem = ((size_t)nmodes * NF + NF) * sizeof(double);
+    if (set_smem(kern, smem)) return -2;
+    const size_t want = (npix + 7) / 8, cap = (size_t)p->sm_count * 4;
+    kern<<<(unsigned)(want < cap ? want : cap), 256, smem, p->stream>>>(cube, d_mean, d_U, nmodes, npix, cleaned, amps);
+    return 0;
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -215,7 +276,18 @@ int fb_pca_project(fb_plan* p, const double* cube, const double* mean, const dou
     FB_CUDA(cudaMemcpyAsync(d_U, U, (size_t)nf * nmodes * sizeof(double), cudaMemcpyDefault, p->stream));
     FB_CUDA(cudaMemcpyAsync(d_mean, mean, nf * sizeof(double), cudaMemcpyDefault, p->stream));
     const unsigned grid = (unsigned)((size_t)p->sm_count * 8 < npix ? (size_t)p->sm_count * 8 : npix);
-    if (nmodes <= 8)
+    if (nmodes <= 8 && nf >= 32 && nf <= 1024) {
+        int rc = 0;
+        switch (nf) {
+            case 32: rc = launch_project_warp<32>(p, cube, d_mean, d_U, nmodes, npix, cleaned, amps); break;
+            case 64: rc = launch_project_warp<64>(p, cube, d_mean, d_U, nmodes, npix, cleaned, amps); break;
+            case 128: rc = launch_project_warp<128>(p, cube, d_mean, d_U, nmodes, npix, cleaned, amps); break;
+            case 256: rc = launch_project_warp<256>(p, cube, d_mean, d_U, nmodes, npix, cleaned, amps); break;
+            case 512: rc = launch_project_warp<512>(p, cube, d_mean, d_U, nmodes, npix, cleaned, amps); break;
+            default: rc = launch_project_warp<1024>(p, cube, d_mean, d_U, nmodes, npix, cleaned, amps); break;
+        }
+        if (rc) return rc;
+    } else if (nmodes <= 8)
         k_pca_project<8><<<grid, 256, 0, p->stream>>>(cube, d_mean, d_U, nf, nmodes, npix, cleaned, amps);
     else
         k_pca_project<32><<<grid, 256, 0, p->stream>>>(cube, d_mean, d_U, nf, nmodes, npix, cleaned, amps);
