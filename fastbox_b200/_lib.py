@@ -67,6 +67,7 @@ SIGNATURES = {
     "fb_mean_spectrum_filter": (_i, [_vp, _vp, _vp, _vp]),
     "fb_pca_covariance": (_i, [_vp, _vp, _vp, _vp]),
     "fb_pca_project": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "fb_bench_fp64": (_i, [_vp, _i, C.POINTER(_d)]),
     "fb_fft_pass_c2c": (_i, [_vp, _vp, _i, _i, _i]),
     "fb_fft_pass_x_c2r": (_i, [_vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
     "fb_fft_pass_x_c2r_gather": (_i, [_vp, _vp, _vp, _vp, _l, _i, _f, C.POINTER(_d)]),
@@ -339,6 +340,12 @@ class Plan(object):
         mean = np.ascontiguousarray(mean, dtype=np.float64)
         check(self.lib.fb_pca_project(self.h, _ptr(cube), mean.ctypes.data, U.ctypes.data, int(U.shape[1]),
                                       _ptr(cleaned), _ptr(amps)))
+
+    def bench_fp64(self, mode=0):
+        """Measured FP64 throughput in TFLOP/s (mode 0: FMA chains, 1: FP64 MMA)."""
+        t = _d(0.0)
+        check(self.lib.fb_bench_fp64(self.h, int(mode), C.byref(t)))
+        return t.value
 
     def fft_pass_c2c(self, data, nplanes, axis_pass, sign):
         check(self.lib.fb_fft_pass_c2c(self.h, _ptr(data), int(nplanes), int(axis_pass), int(sign)))

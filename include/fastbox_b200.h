@@ -197,6 +197,9 @@ int fb_pca_covariance(fb_plan* plan, const double* cube, double* mean_out, doubl
 int fb_pca_project(fb_plan* plan, const double* cube, const double* mean, const double* U, int nmodes,
                    double* cleaned, double* amps);
 
+/* FP64 throughput probe (no memory traffic): mode 0 = FMA chains, 1 = FP64 MMA m8n8k4; TFLOP/s. */
+int fb_bench_fp64(fb_plan* plan, int mode, double* tflops);
+
 /* ---- building blocks exposed for tests / multi-GPU orchestration ---------------- */
 /* pass = 0: rows (z, contiguous) c2c; 1: columns (y) c2c; sign = -1 fwd / +1 inv;
  * data: [nplanes][N][N] complex64, in place.                                   */
