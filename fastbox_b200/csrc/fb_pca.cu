@@ -348,7 +348,8 @@ int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* 
     FB_CUDA(cudaMemsetAsync(d_cov, 0, (size_t)nf * nf * sizeof(double), p->stream));
     const int ntile = (nf + PCA_TILE - 1) / PCA_TILE;
     const int ntri = ntile * (ntile + 1) / 2;
-    int slices = (p->sm_count * 4 + ntri - 1) / ntri;
+    // ~4 full waves at 3 resident CTAs per SM (a grid of 1.5 waves left the second one half empty)
+    int slices = (p->sm_count * 12 + ntri / 2) / ntri;
     const size_t max_slices = (npix + PCA_KT - 1) / PCA_KT;
     if ((size_t)slices > max_slices) slices = (int)max_slices;
     if (slices < 1) slices = 1;
