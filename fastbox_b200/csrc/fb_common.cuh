@@ -170,14 +170,17 @@ __device__ __forceinline__ float2 box_muller(uint32_t x0, uint32_t x1) {
     __sincosf(6.283185307179586f * (((float)x1 + 0.5f) * 2.3283064365386963e-10f) - 3.141592653589793f, &s, &co);
     return make_float2(-r * co, -r * s);             // cos(t) = -cos(t - pi), sin(t) = -sin(t - pi)
 }
-// White noise of the conjugate pair of modes k and -k from ONE Philox4x32-10 block: counter =
-// min(index(k), index(-k)), key = seed; the mode whose linear index is the smaller one takes
-// words (0,1), the other words (2,3).  H(k) = 1/2 [W(k) + conj W(-k)] thus costs one block per
-// mode, on any GPU count (the stream depends only on the global cell index).
-__device__ __forceinline__ void philox_mode_pair(uint64_t seed, uint64_t idx_k, uint64_t idx_mk, float2& wk,
-                                                 float2& wmk) {
-    const uint64_t ctr = idx_k < idx_mk ? idx_k : idx_mk;
-    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+// Hermitian white noise H0(k) = 1/2 [W(k) + conj W(-k)] of a unit complex white field W (box.py:174-176,
+// 187) drawn DIRECTLY, one Box-Muller pair per conjugate pair of modes: for k != -k, H0(k) = (n1 + i n2)/sqrt2
+// and H0(-k) = conj H0(k) (Re and Im of variance 1/2, exactly the law of the Hermitianised reference noise);
+// a self-conjugate mode gets H0 = n1 (real, variance 1).  The pair is identified by its canonical cell index
+// j = min(index(k), index(-k)); Philox4x32-10 block j >> 1 (key = seed) serves two consecutive pairs: words
+// (0,1) for even j, (2,3) for odd j.  The stream depends on the global cell index only (any GPU count).
+__device__ __forceinline__ void philox_block(uint64_t seed, uint64_t ctr, uint32_t (&c)[4]) {
+    c[0] = (uint32_t)ctr;
+    c[1] = (uint32_t)(ctr >> 32);
+    c[2] = 0u;
+    c[3] = 0u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -185,17 +188,26 @@ __device__ __forceinline__ void philox_mode_pair(uint64_t seed, uint64_t idx_k, 
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    const float2 first = box_muller(c[0], c[1]), second = box_muller(c[2], c[3]);
-    if (idx_k == idx_mk) {
-        wk = first;
-        wmk = first;
-    } else if (idx_k < idx_mk) {
-        wk = first;
-        wmk = second;
-    } else {
-        wk = second;
-        wmk = first;
-    }
+}
+// sqrt2 * H0(k) for one mode (generic form: any row, any mode); callers fold the 1/sqrt2 into their multiplier
+__device__ __forceinline__ float2 philox_h0_sqrt2(uint64_t seed, uint64_t idx_k, uint64_t idx_mk) {
+    const uint64_t j = idx_k < idx_mk ? idx_k : idx_mk;
+    uint32_t c[4];
+    philox_block(seed, j >> 1, c);
+    const bool odd = (j & 1u) != 0;
+    const float2 n = box_muller(odd ? c[2] : c[0], odd ? c[3] : c[1]);
+    if (idx_k == idx_mk) return make_float2(1.41421356237309505f * n.x, 0.f);
+    return make_float2(n.x, idx_k < idx_mk ? n.y : -n.y);
+}
+// four consecutive canonical modes j0 .. j0+3 (j0 % 4 == 0, none self-conjugate, none mirrored): two blocks
+__device__ __forceinline__ void philox_h0_sqrt2_quad(uint64_t seed, uint64_t j0, float2 (&h)[4]) {
+    uint32_t c[4];
+    philox_block(seed, j0 >> 1, c);
+    h[0] = box_muller(c[0], c[1]);
+    h[1] = box_muller(c[2], c[3]);
+    philox_block(seed, (j0 >> 1) + 1, c);
+    h[2] = box_muller(c[0], c[1]);
+    h[3] = box_muller(c[2], c[3]);
 }
 
 }  // namespace fb

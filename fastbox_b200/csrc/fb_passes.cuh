@@ -488,7 +488,8 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
     const int ma_ = mode_number(a, N), mb_ = mode_number(b, N);
     const float sab_f = (float)(ma_ * ma_) * A.K.inv_lx2 + (float)(mb_ * mb_) * A.K.inv_ly2;
     const bool dc_row = ma_ == 0 && mb_ == 0;
-    float fast_base = 0.5f;
+    // Philox draws sqrt2 * H0 and the combine doubles it: 1/2 * 1/sqrt2
+    float fast_base = (SRC == SRC_PHILOX) ? 0.35355339059327376f : 0.5f;
     if (fast && (A.flags & FB_F_FILTER)) fast_base *= __ldg(&A.K.tperp[a * N + b]);
 
     bool fast_done = false;
@@ -541,11 +542,20 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
                         mm[e] = make_float2(rm[e], im[e]);
                     }
                 } else {
-                    philox_mode_pair(A.seed, row_g + cq, row_m + cm0, g[0], gm0);
+                    // sqrt2 * H0(k) drawn directly (fb_common.cuh); the 1/sqrt2 sits in fast_base.  Rows with
+                    // row_g < row_m (every plane except a = 0, N/2) hold canonical cells only: two Philox
+                    // blocks per quad.  g = H, y = conj H makes the shared combine below return 2 H.
+                    if (row_g < row_m) {
+                        philox_h0_sqrt2_quad(A.seed, row_g + cq, g);
+                    } else {
 #pragma unroll
-                    for (int e = 1; e < 4; ++e)
-                        philox_mode_pair(A.seed, row_g + cq + e, row_m + mq + 4 - e, g[e], mm[4 - e]);
-                    mm[0] = gm0;
+                        for (int e = 0; e < 4; ++e)
+                            g[e] = philox_h0_sqrt2(A.seed, row_g + cq + e, row_m + ((N - cq - e) & (N - 1)));
+                    }
+                    gm0 = g[0];
+                    gm0.y = -gm0.y;
+#pragma unroll
+                    for (int e = 1; e < 4; ++e) mm[4 - e] = make_float2(g[e].x, -g[e].y);
                 }
                 const float4 tq = has_f ? __ldg(tpar4 + (cq >> 2)) : make_float4(1.f, 1.f, 1.f, 1.f);
                 float am[4] = {tq.x, tq.y, tq.z, tq.w};
@@ -597,10 +607,14 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
                     mm[e] = make_float2(rm[e], im[e]);
                 }
             } else if constexpr (SRC == SRC_PHILOX) {
-                philox_mode_pair(A.seed, row_g + cq, row_m + cm0, g[0], gm0);
 #pragma unroll
-                for (int e = 1; e < 4; ++e) philox_mode_pair(A.seed, row_g + cq + e, row_m + mq + 4 - e, g[e], mm[4 - e]);
-                mm[0] = gm0;
+                for (int e = 0; e < 4; ++e) {                // H0(k) drawn directly; W = H0 is Hermitian
+                    const float2 hs = philox_h0_sqrt2(A.seed, row_g + cq + e, row_m + ((N - cq - e) & (N - 1)));
+                    g[e] = make_float2(0.70710678118654752f * hs.x, 0.70710678118654752f * hs.y);
+                    if (e > 0) mm[4 - e] = cconj(g[e]);
+                }
+                gm0 = cconj(g[0]);
+                (void)mq; (void)cm0;
             } else {
                 load_run<4>(A.src + row_g + cq, g);
                 load_run<4>(A.src + row_m + mq, mm);

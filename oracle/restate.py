@@ -593,8 +593,10 @@ def philox_noise_cube(seed, N):
 
 # --------------------------------------------------------------------------
 # Counter-based white noise (no reference equivalent: the reference draws
-# from NumPy's global MT19937, box.py:174-175).  Philox4x32-10 keyed by
-# (seed, global cell index) + Box-Muller; used for throughput / multi-GPU runs.
+# from NumPy's global MT19937, box.py:174-175): PARITY UNPINNED by construction.
+# Philox4x32-10 keyed by (seed, global cell index) + Box-Muller; the Hermitian part
+# H0 of the white field is drawn directly (it has the law of the reference's
+# 1/2 [W(k) + conj W(-k)]).  Used for throughput / multi-GPU runs.
 # --------------------------------------------------------------------------
 _PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _PH_W0, _PH_W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
@@ -619,24 +621,31 @@ def philox4x32(ctr, key):
 
 def philox_normals(seed, index, N):
     """
-    Two N(0,1) per cell: (re, im) of the white noise W at global linear cell ``index``
-    (uint64 array, index = (a N + b) N + c) of an N^3 grid.  One Philox block serves the conjugate
-    pair of modes k, -k: counter = min(index(k), index(-k)); the cell with the smaller index takes
-    words (0,1), the other words (2,3).
-    u1 = (x0 + 0.5) 2^-32, u2 = (x1 + 0.5) 2^-32, r = sqrt(-2 ln u1), re = r cos(2 pi u2), im = r sin(2 pi u2).
+    (re, im) of the Hermitian white noise H0 = 1/2 [W(k) + conj W(-k)] (box.py:174-176, 187) at global linear
+    cell ``index`` (uint64 array, index = (a N + b) N + c) of an N^3 grid, drawn directly: one Box-Muller pair
+    (n1, n2) per conjugate pair of modes.  Canonical cell j = min(index(k), index(-k)); Philox block j >> 1,
+    key = seed, words (0,1) for even j and (2,3) for odd j;
+    u1 = (x0 + 0.5) 2^-32, u2 = (x1 + 0.5) 2^-32, r = sqrt(-2 ln u1), n1 = r cos(2 pi u2), n2 = r sin(2 pi u2).
+    k != -k: H0(canonical) = (n1 + i n2)/sqrt2, H0(other) = its conjugate; k == -k: H0 = n1 (real).
+    Feeding (re, im) to ``hermitian_half_from_noise`` returns H0 itself (it is already Hermitian).
     """
     index = np.asarray(index, dtype=np.uint64)
     n = np.uint64(N)
     a, b, c = index // (n * n), (index // n) % n, index % n
     mirror = (((n - a) % n) * n + (n - b) % n) * n + (n - c) % n
-    blk = np.minimum(index, mirror)
-    second = index > mirror
+    j = np.minimum(index, mirror)
+    blk = j >> np.uint64(1)
+    odd = (j & np.uint64(1)) != 0
     ctr = np.zeros(index.shape + (4,), dtype=np.uint32)
     ctr[..., 0] = (blk & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     ctr[..., 1] = (blk >> np.uint64(32)).astype(np.uint32)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
     x = philox4x32(ctr, key)
-    u1 = (np.where(second, x[..., 2], x[..., 0]).astype(np.float64) + 0.5) * 2.0 ** -32
-    u2 = (np.where(second, x[..., 3], x[..., 1]).astype(np.float64) + 0.5) * 2.0 ** -32
+    u1 = (np.where(odd, x[..., 2], x[..., 0]).astype(np.float64) + 0.5) * 2.0 ** -32
+    u2 = (np.where(odd, x[..., 3], x[..., 1]).astype(np.float64) + 0.5) * 2.0 ** -32
     r = np.sqrt(-2.0 * np.log(u1))
-    return r * np.cos(TWO_PI * u2), r * np.sin(TWO_PI * u2)
+    n1, n2 = r * np.cos(TWO_PI * u2), r * np.sin(TWO_PI * u2)
+    selfc = index == mirror
+    re = np.where(selfc, n1, n1 * np.sqrt(0.5))
+    im = np.where(selfc, 0.0, np.where(index < mirror, n2, -n2) * np.sqrt(0.5))
+    return re, im

@@ -147,8 +147,17 @@ def test_philox_known_answer():
     ctr = np.full((1, 4), 0xffffffff, np.uint32)
     out = R.philox4x32(ctr, np.full(2, 0xffffffff, np.uint32))
     assert [hex(int(x)) for x in out[0]] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
-    re, im = R.philox_normals(42, np.arange(64 ** 3), 64)
-    assert abs(re.mean()) < 0.01 and abs(re.std() - 1) < 0.01 and abs(np.corrcoef(re, im)[0, 1]) < 0.01
+    # Hermitian white noise drawn directly: Re, Im of variance 1/2, H0(-k) = conj H0(k), 8 real self-conjugate modes
+    N = 32
+    re, im = R.philox_normals(42, np.arange(N ** 3, dtype=np.uint64).reshape(N, N, N), N)
+    assert abs(re.mean()) < 0.01 and abs(re.var() - 0.5) < 0.01 and abs(im.var() - 0.5) < 0.01
+    assert abs(np.corrcoef(re.ravel(), im.ravel())[0, 1]) < 0.02
+    W = re + 1j * im
+    assert np.array_equal(W, np.conj(np.roll(W[::-1, ::-1, ::-1], (1, 1, 1), (0, 1, 2))))
+    assert np.count_nonzero(im == 0.0) == 8
+    assert np.array_equal(R.hermitian_half_from_noise(re, im, np.ones((N // 2 + 1, N, N))), W[:N // 2 + 1])
+    real_field = np.fft.ifftn(W)
+    assert np.abs(real_field.imag).max() < 1e-15 and abs(real_field.real.var() * N ** 3 - 1) < 0.02
 
 
 @pytest.mark.parametrize("name", ["sparse", "dense", "mixed"])
