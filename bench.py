@@ -120,20 +120,6 @@ def configure_plan(plan, N, L):
     return tables, edges
 
 
-def single_gpu_same_workload(N):
-    """Measured one-GPU rate of the sharded workload (profiles/r1_sizes.json): the denominator for strong
-    scaling.  The N=1 bench line runs BASELINE's single-GPU configuration (1024^3, noise resident in HBM)."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_sizes.json")))
-        for r in d["rows"]:
-            if int(r["N"]) == int(N):
-                return {"value": r["philox_Gcells_s"] * 1e3, "unit": "Mcells/s", "ms_per_step": r["philox_ms"],
-                        "source": "profiles/r1_sizes.json (tools/bench_sizes.py, Philox noise, one B200)"}
-    except Exception:
-        pass
-    return None
-
-
 def upload_tables(plan, t):
     plan.set_sqrt_pk(t["lut"], *t["lut_mode"])
     plan.set_filter(t["tperp"], t["tpar"], None)
@@ -141,36 +127,45 @@ def upload_tables(plan, t):
 
 
 def cpu_port_step(N, L, seed=11):
-    """One step of the reference algorithm on the CPU (oracle port): returns seconds."""
+    """One step of the reference algorithm on the CPU (oracle port), as CosmoBox.realise_density runs it:
+    the white-noise draw (box.py:174-175) and the k grid (box.py:116-127) are inside the timed region."""
     from oracle import restate as R
     from _util import pk_function
     _, pkf = pk_function(Z_BOX)
-    rng = np.random.RandomState(seed)
-    re = rng.normal(0., 1., (N, N, N))
-    im = rng.normal(0., 1., (N, N, N))
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         t0 = time.perf_counter()
+        rng = np.random.RandomState(seed)
+        re = rng.normal(0., 1., (N, N, N))                                        # box.py:174
+        im = rng.normal(0., 1., (N, N, N))                                        # box.py:175
         dx, dk = R.realise_density_port(re, im, pkf, N, L, L, L)                  # box.py:161-193
         filt = R.apply_transfer_fn_port(dk, transfer_fn, N, L, L, L)               # box.py:374-380
         R.binned_power_spectrum_port(np.fft.fftn(filt.real), N, L, L, L, nbins=NBINS)   # box.py:736-768
         return time.perf_counter() - t0
 
 
+CPU_SAMPLE_N = 256       # one bounded box of the workload per CPU step (the reference cannot hold 1024^3)
+
+
+def cpu_sample_text(n, extra=""):
+    return ("%d^3 box per step: NumPy port of fastbox/box.py realise_density (incl. its np.random draws and k grid) + "
+            "apply_transfer_fn + binned_power_spectrum, float64; numpy.fft is single-threaded as in the reference; "
+            "the reference cannot hold 1024^3 (~140 GB of float64 temporaries); host has %d cores%s"
+            % (n, os.cpu_count() or 0, extra))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_ref = 256 if (args.steps + args.warmup) <= 4 else 128
+    n_ref = CPU_SAMPLE_N
     L = 2000.0 * n_ref / 1024.0
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):
         cpu_port_step(n_ref, L)
-    ts = [cpu_port_step(n_ref, L) for _ in range(args.steps)]
+    ts = [cpu_port_step(n_ref, L, seed=11 + i) for i in range(args.steps)]
     t = float(np.mean(ts))
     val = n_ref ** 3 / t / 1e6
-    sample = ("%d^3 box per step (NumPy port of fastbox/box.py realise_density + apply_transfer_fn + "
-              "binned_power_spectrum, float64, numpy.fft is single-threaded as in the reference; the reference "
-              "cannot hold 1024^3 in host RAM)" % n_ref)
+    sample = cpu_sample_text(n_ref)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -180,6 +175,30 @@ def run_reference(args, rank):
             "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def one_gpu_sharded_workload(N, L, dev, steps=3):
+    """LIVE one-GPU rate of the workload the multi-GPU lines shard (N^3, Philox noise): the strong-scaling
+    denominator.  Needs 8 N^3 bytes (68 GB at 2048^3)."""
+    from fastbox_b200 import _lib
+    plan = _lib.Plan(N, L, L, L, dev)
+    try:
+        configure_plan(plan, N, L)
+        field = plan.alloc(N ** 3 * 4)
+        flags = _lib.F_SQRTPK | _lib.F_FILTER
+        plan.realise(None, None, seed=1, flags=flags, field_out=field, want_pk=True)
+        plan.sync()
+        plan.timer_start()
+        for it in range(steps):
+            plan.realise(None, None, seed=it, flags=flags, field_out=field, want_pk=True)
+        ms = plan.timer_stop() / steps
+        field.free()
+        return {"value": N ** 3 / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms, "steps": steps,
+                "source": "measured live in this run on one GPU (%d^3, Philox noise, same tables)" % N}
+    except Exception as exc:      # pragma: no cover
+        return {"value": None, "error": str(exc)}
+    finally:
+        plan.close()
 
 
 def run_single(args):
@@ -327,9 +346,14 @@ def run_single(args):
         ts_cpu = [cpu_port_step(n_cpu, 2000.0 * n_cpu / 1024.0, seed=11 + i) for i in range(2)]
         t_cpu = float(np.mean(ts_cpu))
         cpu = {"value": n_cpu ** 3 / t_cpu / 1e6, "unit": "Mcells/s", "cores": 1, "kind": "port",
-               "sample": "two %d^3 boxes (%.1f s in total): NumPy port of fastbox/box.py realise_density + "
-                         "apply_transfer_fn + binned_power_spectrum, float64; numpy.fft is single-threaded as "
-                         "shipped; host has %d cores" % (n_cpu, sum(ts_cpu), os.cpu_count() or 0)}
+               "sample": cpu_sample_text(n_cpu, "; two steps, %.1f s in total" % sum(ts_cpu))}
+
+    # ---- the workload the multi-GPU lines shard (2048^3, Philox), measured live on this one GPU
+    sharded = None
+    if not args.no_one_gpu and N == 1024:
+        del re, im, field
+        torch.cuda.empty_cache()
+        sharded = one_gpu_sharded_workload(args.size_multi, 2000.0 * args.size_multi / 1024.0, dev)
 
     line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -337,11 +361,172 @@ def run_single(args):
             "config": {"workload": "%d^3 realise + k_perp/k_par filter + binned P(k) (nbins=%d), white noise "
                                    "resident in HBM" % (N, NBINS),
                        "box_Mpc": L, "redshift": Z_BOX,
-                       "l2": "inputs (%.1f GB noise) larger than L2 (126 MB); no flush needed" % (8 * n3 / 1e9)},
+                       "l2": "inputs (%.1f GB noise) larger than L2 (126 MB); no flush needed" % (8 * n3 / 1e9),
+                       "sharded_workload_on_one_gpu": sharded},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu}
     print(json.dumps(line))
     plan.close()
+
+
+def run_config(args):
+    """
+    BASELINE.json configs[1..3] as stage-by-stage device-resident pipelines (one JSON line): every stage is one
+    C-ABI call on buffers resident in HBM, timed with CUDA events on the library stream; bytes/cell are the
+    algorithmic figures of SURVEY section 8(d).
+    """
+    import torch
+    from fastbox_b200 import _lib
+    F = _lib
+    name = args.config
+    N = 512 if name == "lognormal_rsd_512" else 1024
+    L = 2000.0
+    dev = 0
+    torch.cuda.set_device(dev)
+    plan = _lib.Plan(N, L, L, L, dev)
+    configure_plan(plan, N, L)
+    hbm_peak, peak_src = measured_peaks()
+    n3 = N ** 3
+    nh = (N // 2 + 1) * N * N
+    g = torch.Generator(device="cuda")
+    g.manual_seed(41)
+    re = torch.randn(n3, device="cuda", dtype=torch.float32, generator=g)
+    im = torch.randn(n3, device="cuda", dtype=torch.float32, generator=g)
+    field, f2, f3 = (plan.alloc(n3 * 4) for _ in range(3))
+    spec = plan.alloc(nh * 8)
+    zgrid = np.linspace(-0.5 * L, 0.5 * L, N)
+    bias = 0.84081272                                    # HITracer.bias_HI(0.8) (tracers.py:129-144)
+    stages = []
+
+    def stage(label, bytes_per_cell, fn):
+        stages.append((label, bytes_per_cell, fn))
+
+    if name == "lognormal_rsd_512":
+        # example_endtoend.py:27-44: realise -> b delta -> log-normal -> v_z -> redshift-space remap
+        stage("realise_density + store delta_k (box.py:161-193)", 32,
+              lambda: plan.realise(re, im, flags=F.F_SQRTPK, field_out=field, spec_out=spec, want_sums=False))
+        st = {}
+        stage("bias + exp from delta_k (tracers.py:129-144, box.py:457)", 24,
+              lambda: st.__setitem__("s", plan.spectrum_to_field(spec, f2, flags=F.F_EXP, scale=bias)[0]))
+        stage("log-normal normalise (box.py:458-459)", 8,
+              lambda: plan.affine(f2, n3, 1.0 / (st["s"] / n3), -1.0))
+        stage("v_z = Re ifftn(velocity_k[2]) (box.py:254-285)", 24,
+              lambda: plan.spectrum_to_field(spec, f3, kind=F.KIND_VEL_Z, scale=57.3))
+        stage("redshift_space_density (box.py:412-437)", 12, lambda: plan.rsd_remap(f2, f3, None, zgrid, 100.0, field))
+    elif name == "filter_beam_poles_1024":
+        x = torch.arange(N, device="cuda", dtype=torch.float32) - N / 2.
+        sig = (1.5 + 4.0 * torch.arange(N, device="cuda", dtype=torch.float32) / N)
+        beam = torch.exp(-0.5 * (x[:, None, None] ** 2 + x[None, :, None] ** 2) / sig[None, None, :] ** 2).contiguous()
+        stage("realise + k_perp/k_par filter (box.py:161-193, 374-380)", 28,
+              lambda: plan.realise(re, im, flags=F.F_SQRTPK | F.F_FILTER, field_out=field, want_sums=False))
+        stage("BeamModel.convolve_fft (beams.py:81-87)", 40, lambda: plan.beam_convolve(beam, field, f2))
+        stage("binned P(k) + l = 2, 4 multipoles of the observed field (box.py:736-764 ext.)", 20,
+              lambda: plan.field_to_spectrum(f2, want_pk=True, poles=True))
+    else:
+        # example_halos.py:20-53: log-normal field -> Poisson halo counts -> cross P(k) with the 21cm field
+        u = torch.rand(n3, device="cuda", dtype=torch.float64, generator=g)
+        counts = plan.alloc(n3 * 4)
+        nbar = np.array([1e-3], np.float32)
+        b1 = np.array([1.0], np.float32)
+        lam_bar = 1e-3 * L ** 3 / n3
+        st = {}
+        stage("realise_density + store delta_k (box.py:161-193)", 32,
+              lambda: plan.realise(re, im, flags=F.F_SQRTPK, field_out=field, spec_out=spec, want_sums=False))
+        stage("exp(delta) from delta_k (box.py:457)", 24,
+              lambda: st.__setitem__("s", plan.spectrum_to_field(spec, f2, flags=F.F_EXP, scale=1.0)[0]))
+        stage("log-normal normalise (box.py:458-459)", 8, lambda: plan.affine(f2, n3, 1.0 / (st["s"] / n3), -1.0))
+        stage("halo_count_field, Poisson inversion (halos.py:91-117)", 16,
+              lambda: plan.halo_counts(f2, nbar, 0, b1, 0, False, 0.0, u, counts))
+        stage("halo overdensity N_h / N_bar - 1", 8, lambda: plan.counts_to_field(counts, n3, 1.0 / lam_bar, -1.0, f3))
+        stage("cross P(k) of the halo field with delta_k (example_halos.py:46-53)", 24,
+              lambda: st.__setitem__("pk", plan.field_to_spectrum(f3, cross=spec, want_pk=True)))
+
+    for _ in range(max(1, args.warmup)):
+        for _, _, fn in stages:
+            fn()
+    plan.sync()
+    per = np.zeros(len(stages))
+    launches0 = _lib.launch_count()
+    with ClockSampler(dev) as clk:
+        plan.timer_start()
+        for _ in range(args.steps):
+            for _, _, fn in stages:
+                fn()
+        total_ms = plan.timer_stop() / args.steps
+        for i, (_, _, fn) in enumerate(stages):                      # per-stage times, measured separately
+            plan.timer_start()
+            for _ in range(3):
+                fn()
+            per[i] = plan.timer_stop() / 3
+    launches = _lib.launch_count() - launches0
+    bpc = float(sum(b for _, b, _ in stages))
+    rows = [{"stage": lab, "ms": float(ms), "bytes_per_cell": b, "GBs": b * n3 / (ms * 1e-3) / 1e9,
+             "frac_hbm": b * n3 / (ms * 1e-3) / 1e9 / hbm_peak} for (lab, b, _), ms in zip(stages, per)]
+    dom = int(np.argmax(per))
+    line = {"metric": "Mcells/s " + name, "value": n3 / (total_ms * 1e-3) / 1e6, "unit": "Mcells/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d^3, every stage one C-ABI call on HBM-resident buffers" % (name, N),
+                       "box_Mpc": L, "l2": "all cubes (%.1f GB each) larger than L2" % (4 * n3 / 1e9)},
+            "stages": rows, "clocks": clk.summary(), "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": rows[dom]["stage"], "achieved": rows[dom]["GBs"], "peak": hbm_peak,
+                         "unit": "GB/s", "frac": rows[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                         "pipeline": {"bytes_per_cell": bpc, "achieved": bpc * n3 / (total_ms * 1e-3) / 1e9,
+                                      "frac": bpc * n3 / (total_ms * 1e-3) / 1e9 / hbm_peak}},
+            "e2e": None, "cpu_baseline": None}
+    print(json.dumps(line))
+    plan.close()
+
+
+def multi_gpu_check(rank, world, local_rank, mode):
+    """
+    Correctness of the sharded path inside the bench run (SCALE lines carry it): a 256^3 box realised over all
+    ranks equals the same box realised on one GPU -- field bit for bit, bin populations exactly, moments to 1e-12.
+    """
+    import torch
+    import torch.distributed as dist
+    from fastbox_b200 import _lib
+    from fastbox_b200 import dist as fbd
+    N = 256
+    L = 2000.0 * N / 1024.0
+    flags = _lib.F_SQRTPK | _lib.F_FILTER
+    if mode == "p2p":
+        dr = fbd.NvlinkRealiser(N, (L, L, L), rank, world, local_rank, chunks=2, with_forward=True)
+        configure_plan(dr.plan, N, L)
+        for _ in range(2):
+            _, pk, _ = dr.realise(5, flags, want_pk=True)
+        fwd = dr.power_spectrum()
+        slab = torch.from_numpy(dr.field_host()).cuda()
+        plan_close = dr.close
+    else:
+        eng = fbd.CudaEngine(N, (L, L, L), rank, world, local_rank, chunks=1)
+        configure_plan(eng.plan, N, L)
+        dn = fbd.DistributedRealiser(eng)
+        slab, pk, _ = dn.realise(5, flags, want_pk=True)
+        torch.cuda.synchronize()
+        fwd = dn.power_spectrum()
+        slab = slab.clone()
+        plan_close = eng.plan.close
+    parts = [torch.empty_like(slab) for _ in range(world)]
+    dist.all_gather(parts, slab)
+    out = None
+    if rank == 0:
+        full = torch.cat(parts, dim=1).cpu().numpy()
+        plan = _lib.Plan(N, L, L, L, local_rank)
+        configure_plan(plan, N, L)
+        ref = np.empty((N, N, N), np.float32)
+        res, _ = plan.realise(None, None, seed=5, flags=flags, field_out=ref, want_pk=True)
+        fref = plan.field_to_spectrum(ref, want_pk=True)
+        plan.close()
+        nz = res["sum1"] != 0
+        out = {"size": N, "field_bit_identical_to_1gpu": bool(np.array_equal(full, ref)),
+               "field_rel_l2_vs_1gpu": float(np.linalg.norm(full.astype(np.float64) - ref) / np.linalg.norm(ref)),
+               "pk_counts_equal": bool(np.array_equal(pk["count"], res["count"])),
+               "pk_sum1_max_rel_err": float(np.max(np.abs(pk["sum1"][nz] - res["sum1"][nz]) / np.abs(res["sum1"][nz]))),
+               "forward_pk_counts_equal": bool(np.array_equal(fwd["count"], fref["count"])),
+               "forward_pk_sum1_max_rel_err": float(np.max(np.abs(fwd["sum1"][nz] - fref["sum1"][nz]) / np.abs(fref["sum1"][nz])))}
+    plan_close()
+    return out
 
 
 def run_multi(args, rank, world, local_rank):
@@ -352,20 +537,41 @@ def run_multi(args, rank, world, local_rank):
     N = args.size_multi
     L = 2000.0 * N / 1024.0
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")       # NCCL kernels must not queue behind our grids
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    mode = os.environ.get("FB_DIST_MODE", "p2p")           # p2p: exchange inside the library; nccl: all_to_all_single
     chunks = int(os.environ.get("FB_CHUNKS", "4"))
     while chunks > 1 and ((N // 2) // world) % chunks:
         chunks //= 2
-    eng = fbd.CudaEngine(N, (L, L, L), rank, world, local_rank, chunks=chunks)
-    configure_plan(eng.plan, N, L)
-    dr = fbd.DistributedRealiser(eng)
     flags = _lib.F_SQRTPK | _lib.F_FILTER
+    hbm_peak, peak_src = measured_peaks()
 
-    def step(seed):
-        if chunks > 1:
-            return dr.realise_overlapped(seed, flags, want_pk=True)
-        return dr.realise(seed, flags, want_pk=True)
+    # live one-GPU rate of the very same workload (rank 0, before the sharded buffers exist)
+    one_gpu = one_gpu_sharded_workload(N, L, local_rank) if (rank == 0 and not args.no_one_gpu) else None
+    dist.barrier()
+    check = multi_gpu_check(rank, world, local_rank, mode)
+    dist.barrier()
+
+    pass_ms = np.zeros(3)
+    if mode == "p2p":
+        dr = fbd.NvlinkRealiser(N, (L, L, L), rank, world, local_rank, chunks=chunks, with_forward=False)
+        plan = dr.plan
+        configure_plan(plan, N, L)
+
+        def step(seed):
+            return dr.realise(seed, flags, want_pk=True)
+        field_dev = dr.field
+    else:
+        eng = fbd.CudaEngine(N, (L, L, L), rank, world, local_rank, chunks=chunks)
+        plan = eng.plan
+        configure_plan(plan, N, L)
+        dn = fbd.DistributedRealiser(eng)
+
+        def step(seed):
+            out = dn.realise_overlapped(seed, flags, want_pk=True) if chunks > 1 else dn.realise(seed, flags, want_pk=True)
+            eng.sync()
+            return out
+        field_dev = eng.field
 
     for w in range(args.warmup):
         step(w)
@@ -374,87 +580,109 @@ def run_multi(args, rank, world, local_rank):
     dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    xev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clk:
-        # the library stream is host-synchronised around every hand-over to torch's stream, so
-        # events on torch's stream bracket all device work of the steps
+        # every step ends with a host synchronisation of the library stream (the P(k) read-back), so events
+        # on torch's stream bracket all device work of the steps
         ev0.record()
-        for s in range(args.steps):
-            if chunks > 1:
-                step(s)
-                eng.sync()
-            else:
-                eng.realise_kspace(s, flags, True)
-                eng.sync()
-                xev[s][0].record()
-                dr.exchange()
-                xev[s][1].record()
-                eng.sync_exchange()
-                eng.x_to_real()
-                eng.sync()
+        for s_ in range(args.steps):
+            _, pk, _ = step(s_)
+            if mode == "p2p":
+                pass_ms += np.array(plan.last_timings(3))
         ev1.record()
         torch.cuda.synchronize()
     t_wall = ev0.elapsed_time(ev1) * 1e-3
-    # the exchange alone (whole half spectrum, not overlapped), for the NVLink roofline
-    xs = []
-    for _ in range(3):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = _lib.launch_count() - launches0
+    pass_ms /= args.steps
+
+    # result checks on the full-size box itself: every mode binned once, Parseval (box.py:944-946)
+    if mode == "p2p":
+        _, pk, sums = dr.realise(0, flags, want_pk=True, want_sums=True)
+        sumsq = torch.tensor([sums[1]], device="cuda", dtype=torch.float64)
+    else:
+        out = step(0)
+        pk = out[1]
+        sumsq = torch.tensor([out[2][1]], device="cuda", dtype=torch.float64)
+    dist.all_reduce(sumsq)
+    parseval = float(sumsq[0]) * N ** 3 / (float(pk["sum1"].sum()) * (N ** 6. / L ** 3))
+
+    # the exchange alone, for the NVLink roofline
+    a2a = max(fbd.alltoall_bytes_per_rank(N, world))
+    if mode == "p2p":
         dist.barrier()
-        torch.cuda.synchronize()
-        a.record()
-        dr.exchange()
-        b.record()
-        torch.cuda.synchronize()
-        xs.append(a.elapsed_time(b) * 1e-3)
-    t_x_alone = min(xs)
+        t_x_alone = plan.dist_bench_exchange(3) * 1e-3
+    else:
+        xs = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            a.record()
+            dn.exchange()
+            b.record()
+            torch.cuda.synchronize()
+            xs.append(a.elapsed_time(b) * 1e-3)
+        t_x_alone = min(xs)
+
     # end to end: every step also brings the rank's field slab to pinned host memory
-    host_slab = torch.empty(eng.field.shape, dtype=torch.float32, pin_memory=True)
+    ny = N // world
+    host_slab = plan.host_alloc((N, ny, N), np.float32)
     e2e_steps = max(2, min(args.steps, 4))
     step(0)
-    host_slab.copy_(eng.field, non_blocking=False)
+    _lib.check(plan.lib.fb_copy(plan.h, host_slab.ctypes.data, _lib._ptr(field_dev), host_slab.nbytes))
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for s_ in range(e2e_steps):
         step(s_)
-        eng.sync()
-        host_slab.copy_(eng.field, non_blocking=False)
+        _lib.check(plan.lib.fb_copy(plan.h, host_slab.ctypes.data, _lib._ptr(field_dev), host_slab.nbytes))
     torch.cuda.synchronize()
     dist.barrier()
     t_e2e = (time.perf_counter() - t0) / e2e_steps
-    t_x = sum(a.elapsed_time(b) for a, b in xev) * 1e-3 if chunks == 1 else 0.0
-    dist.barrier()
-    t = torch.tensor([t_wall, t_x, t_x_alone, t_e2e], device="cuda", dtype=torch.float64)
+    t = torch.tensor([t_wall, t_x_alone, t_e2e] + list(pass_ms), device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_wall, t_x, t_x_alone, t_e2e = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    launches = _lib.launch_count() - launches0
+    t_wall, t_x_alone, t_e2e = float(t[0]), float(t[1]), float(t[2])
+    pass_ms = [float(x) for x in t[3:6]]
     if rank == 0:
         ms_step = t_wall / args.steps * 1e3
         value = N ** 3 / (ms_step * 1e-3) / 1e6
-        hbm_peak, peak_src = measured_peaks()
-        a2a = max(fbd.alltoall_bytes_per_rank(N, world))
         nv = a2a / t_x_alone / 1e9
+        check = dict(check or {}, count_sum=int(pk["count"].sum()), count_sum_expected=N ** 3,
+                     count_sum_ok=bool(int(pk["count"].sum()) == N ** 3), parseval_ratio=parseval)
+        how = ("exchange inside the library: the y pass stores straight into the peers' receive buffers over "
+               "NVLink (CUDA IPC), %d first-pass chunks overlap the stores, device-side epoch flags, no NCCL on "
+               "the data path" % chunks) if mode == "p2p" else \
+              ("one NCCL all_to_all_single in %d chunks overlapped with the k-space passes" % chunks)
+        nvlink = {"bytes_sent_per_gpu": a2a, "exchange_alone_ms": t_x_alone * 1e3, "achieved_GBs": nv,
+                  "frac_of_900": nv / 900.0, "frac_of_measured_770": nv / 770.0, "mode": mode}
+        if mode == "p2p":
+            nvlink.update({"in_pipeline": {"kspace_passes_with_peer_stores_ms": pass_ms[0], "wait_for_peers_ms": pass_ms[1],
+                                           "x_pass_ms": pass_ms[2],
+                                           "note": "max over ranks of the per-step means; the first segment contains "
+                                                   "the first pass, the y pass and its NVLink stores"},
+                           "in_pipeline_GBs": a2a / (pass_ms[0] * 1e-3) / 1e9 if pass_ms[0] > 0 else None})
         line = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "%d^3 realise + filter + binned P(k), Philox noise, slab decomposition over "
-                                       "%d GPUs, one NCCL all-to-all in %d chunks overlapped with the k-space passes" % (N, world, chunks),
+                                       "%d GPUs; %s" % (N, world, how),
                            "box_Mpc": L,
                            "l2": "per-GPU working set %.1f GB >> L2" % (12.0 * N ** 3 / world / 1e9),
-                           "same_workload_on_one_gpu": single_gpu_same_workload(N)},
+                           "same_workload_on_one_gpu": one_gpu},
+                "check": check,
                 "clocks": clk.summary(), "gpu_launches": int(launches),
-                "e2e": {"value": N ** 3 / t_e2e / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 0,
+                "e2e": {"value": N ** 3 / t_e2e / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": 8,
                         "d2h_bytes_per_step": 4 * N ** 3 + world * 3 * 8 * (NBINS + 1), "ms_per_step": t_e2e * 1e3,
-                        "note": "Philox noise is generated on the device (seed is the only input); every step each "
-                                "rank copies its field slab to pinned host memory and reads back the P(k) moments"},
+                        "note": "Philox noise is generated on the device (the 8-byte seed is the only input); every "
+                                "step each rank copies its field slab to pinned host memory and reads back the P(k) "
+                                "moments"},
                 "roofline": {"bound": "hbm", "achieved": BYTES_PER_CELL_PHILOX * N ** 3 / world / (ms_step * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": BYTES_PER_CELL_PHILOX * N ** 3 / world / (ms_step * 1e-3) / 1e9 / hbm_peak,
-                             "traffic": None, "peak_source": peak_src,
-                             "nvlink": {"bytes_sent_per_gpu": a2a, "exchange_ms": t_x_alone * 1e3, "overlapped_chunks": chunks,
-                                        "achieved_GBs": nv, "frac_of_900": None if nv is None else nv / 900.0,
-                                        "frac_of_measured_770": None if nv is None else nv / 770.0}},
+                             "traffic": None, "peak_source": peak_src, "nvlink": nvlink},
                 "cpu_baseline": None}
+        if one_gpu and one_gpu.get("value"):
+            line["strong_scaling_vs_live_one_gpu"] = {"speedup": value / one_gpu["value"],
+                                                      "efficiency": value / one_gpu["value"] / world}
         print(json.dumps(line))
     dist.destroy_process_group()
 
@@ -467,7 +695,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="grid size for the single-GPU run")
     ap.add_argument("--size-multi", type=int, default=2048, help="grid size for the multi-GPU run")
-    ap.add_argument("--cpu-size", type=int, default=256)
+    ap.add_argument("--cpu-size", type=int, default=CPU_SAMPLE_N)
+    ap.add_argument("--no-one-gpu", action="store_true", help="skip the live one-GPU run of the sharded workload")
+    ap.add_argument("--config", default="headline",
+                    choices=["headline", "lognormal_rsd_512", "filter_beam_poles_1024", "halos_cross_1024"],
+                    help="BASELINE.json configs[1..3] as stage-by-stage pipelines (one JSON line each)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -479,6 +711,8 @@ def main():
         return
     if world > 1:
         run_multi(args, rank, world, local_rank)
+    elif args.config != "headline":
+        run_config(args)
     else:
         run_single(args)
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "fb_launch_count": (_u64, []),
     "fb_plan_set_slab": (_i, [_vp, _i, _i, _i, _i]),
     "fb_dev_alloc": (_i, [C.POINTER(_vp), _sz]),
+    "fb_dev_alloc_on": (_i, [_i, C.POINTER(_vp), _sz]),
     "fb_dev_free": (_i, [_vp]),
     "fb_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "fb_host_free": (_i, [_vp]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "fb_rsd_remap": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp]),
     "fb_beam_convolve": (_i, [_vp, _vp, _vp, _vp]),
     "fb_halo_counts": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
+    "fb_counts_to_field": (_i, [_vp, _vp, _sz, _f, _f, _vp]),
     "fb_halo_catalogue": (_i, [_vp, _vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "fb_fg_cube": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i]),
     "fb_radiometer_noise": (_i, [_vp, _vp, _vp, _u64, _vp, _i]),
@@ -74,6 +76,15 @@ SIGNATURES = {
     "fb_fft_pass_x_r2c": (_i, [_vp, _vp, _vp, _l]),
     "fb_realise_local_kspace": (_i, [_vp, _u64, _i, _vp, _vp, _i, C.POINTER(PkResult)]),
     "fb_forward_local_kspace": (_i, [_vp, _vp, _vp, _i, _vp, _i, C.POINTER(PkResult)]),
+    "fb_dist_init": (_i, [_vp, _i, _i, _i]),
+    "fb_dist_get_handle": (_i, [_vp, _vp]),
+    "fb_dist_connect": (_i, [_vp, _vp]),
+    "fb_dist_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i),
+                          C.POINTER(_i), C.POINTER(_sz)]),
+    "fb_dist_barrier": (_i, [_vp]),
+    "fb_dist_realise": (_i, [_vp, _u64, _i, _f, _i, _i, _vp, C.POINTER(PkResult), C.POINTER(_d)]),
+    "fb_dist_bench_exchange": (_i, [_vp, _i, C.POINTER(_f)]),
+    "fb_dist_power_spectrum": (_i, [_vp, _vp, _i, _i, C.POINTER(PkResult)]),
     "fb_bench_strided_copy": (_i, [_vp, _sz, _i, _i, C.POINTER(_d)]),
     "fb_last_timings": (_i, [_vp, C.POINTER(_f), _i]),
     "fb_timer_start": (_i, [_vp]),
@@ -124,11 +135,15 @@ def _ptr(x):
 class DeviceBuffer(object):
     """Owning handle of device memory allocated through the C ABI."""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, device=None):
         p = C.c_void_p()
-        check(load().fb_dev_alloc(C.byref(p), max(int(nbytes), 16)))
+        if device is None:
+            check(load().fb_dev_alloc(C.byref(p), max(int(nbytes), 16)))
+        else:
+            check(load().fb_dev_alloc_on(int(device), C.byref(p), max(int(nbytes), 16)))
         self.ptr = p.value
         self.nbytes = int(nbytes)
+        self.device = device
 
     def free(self):
         if self.ptr:
@@ -175,11 +190,11 @@ class Plan(object):
 
     # -- memory -------------------------------------------------------------
     def alloc(self, nbytes):
-        return DeviceBuffer(nbytes)
+        return DeviceBuffer(nbytes, self.device)
 
     def upload(self, arr, dtype=None):
         a = np.ascontiguousarray(arr, dtype=dtype)
-        buf = DeviceBuffer(a.nbytes)
+        buf = DeviceBuffer(a.nbytes, self.device)
         check(self.lib.fb_copy(self.h, buf.ptr, a.ctypes.data, a.nbytes))
         return buf
 
@@ -189,7 +204,7 @@ class Plan(object):
         if a.dtype == np.float32:
             return self.upload(a)
         a = np.ascontiguousarray(a, dtype=np.float64)
-        buf = DeviceBuffer(a.size * 4)
+        buf = DeviceBuffer(a.size * 4, self.device)
         check(self.lib.fb_convert_f64_to_f32(self.h, a.ctypes.data, buf.ptr, a.size))
         return buf
 
@@ -300,6 +315,9 @@ class Plan(object):
                                       int(bool(lognormal)), float(mean_exp), _ptr(uniforms), _ptr(counts_out),
                                       _ptr(mean_out)))
 
+    def counts_to_field(self, counts, n, mul, add, out):
+        check(self.lib.fb_counts_to_field(self.h, _ptr(counts), int(n), float(mul), float(add), _ptr(out)))
+
     def halo_catalogue(self, counts, uniforms=None, cat_out=None, capacity=0):
         """Rows of the catalogue of `counts` (int32 [N^3]); with cat_out (float64 [capacity][3]) also fills it."""
         nh = _u64(0)
@@ -374,6 +392,52 @@ class Plan(object):
         st, res = (self._pk_struct(poles) if want_pk else (None, None))
         check(self.lib.fb_forward_local_kspace(self.h, _ptr(recv), _ptr(work), int(ny), _ptr(spec_out),
                                                F_POLES if poles else 0, C.byref(st) if st is not None else None))
+        return res
+
+    # -- multi-GPU (exchange inside the library) ---------------------------------
+    DIST_HANDLE_BYTES = 128
+
+    def dist_init(self, rank, world, with_forward=True):
+        check(self.lib.fb_dist_init(self.h, int(rank), int(world), int(bool(with_forward))))
+
+    def dist_handle(self):
+        buf = np.zeros(self.DIST_HANDLE_BYTES, dtype=np.uint8)
+        check(self.lib.fb_dist_get_handle(self.h, buf.ctypes.data))
+        return buf
+
+    def dist_connect(self, handles):
+        h = np.ascontiguousarray(handles, dtype=np.uint8)
+        check(self.lib.fb_dist_connect(self.h, h.ctypes.data))
+
+    def dist_info(self):
+        v = [C.c_int() for _ in range(6)]
+        nb = C.c_size_t()
+        check(self.lib.fb_dist_info(self.h, *[C.byref(x) for x in v], C.byref(nb)))
+        return dict(zip(("rank", "world", "a0", "na", "y0", "ny"), [x.value for x in v]), block_bytes=nb.value)
+
+    def dist_barrier(self):
+        check(self.lib.fb_dist_barrier(self.h))
+
+    def dist_realise(self, seed, flags, field_out, scale=1.0, chunks=4, phase=0, want_pk=False, want_sums=False):
+        st, res = (self._pk_struct(False) if want_pk else (None, None))
+        sums = (C.c_double * 2)()
+        check(self.lib.fb_dist_realise(self.h, int(seed), int(flags), float(scale), int(chunks), int(phase),
+                                       _ptr(field_out), C.byref(st) if st is not None else None,
+                                       sums if want_sums else None))
+        return res, (sums[0], sums[1])
+
+    def dist_bench_exchange(self, iters=3):
+        ms = C.c_float()
+        check(self.lib.fb_dist_bench_exchange(self.h, int(iters), C.byref(ms)))
+        return float(ms.value)
+
+    def dist_power_spectrum(self, field, poles=False, phase=0, res=None):
+        """``res`` (from an earlier phase of the same step) is filled when the step completes."""
+        if res is None:
+            st, out = self._pk_struct(poles)
+            res = dict(out, _st=st)
+        check(self.lib.fb_dist_power_spectrum(self.h, _ptr(field), F_POLES if poles else 0, int(phase),
+                                              C.byref(res["_st"])))
         return res
 
     def bench_strided_copy(self, total_bytes, chunk_bytes, iters=5):

@@ -65,6 +65,7 @@ class DeviceSpectrum(object):
             m = np.concatenate([m[:, :1], m[:, :0:-1]], axis=1)
             m = np.concatenate([m[:, :, :1], m[:, :, :0:-1]], axis=2)
             full[h:] = m
+            full.setflags(write=False)      # the device copy is the master: an in-place edit would not reach it
             self._full = full
         return self._full if dtype is None else self._full.astype(dtype)
 
@@ -109,6 +110,10 @@ class CosmoBox(object):
         if not isinstance(cosmo, ccl.Cosmology):
             raise TypeError("`cosmo` must be a CCL Cosmology object or dict.")
         self.cosmo = cosmo
+        if int(nsamp) != nsamp or nsamp < 8 or nsamp > 2048 or (int(nsamp) & (int(nsamp) - 1)):
+            raise ValueError("nsamp=%r: the GPU path needs a power of two in [8, 2048] (the reference accepts any "
+                             "size; see INTEGRATION.md, limits)" % (nsamp,))
+        self.backend_name = ccl.name            # "pyccl" or "builtin-eh98" (cosmology.get_backend)
         self.N = nsamp
         self.redshift = redshift
         self.scale_factor = 1. / (1. + redshift)
@@ -139,6 +144,7 @@ class CosmoBox(object):
         self._bins_key = None
         self._d_delta_x = None          # device float32 field matching self.delta_x
         self._delta_x_host = None
+        self._delta_x_sig = None
 
         if realise_now:
             self.realise_density()
@@ -251,12 +257,22 @@ class CosmoBox(object):
         if isinstance(arr, _lib.DeviceBuffer):
             return arr
         if arr is self._delta_x_host and self._d_delta_x is not None:
-            return self._d_delta_x
+            # zero-copy reuse only while the host array still holds what was downloaded: an in-place edit
+            # (box.delta_x *= b, box.delta_x[mask] = 0) must reach the device like it reaches the reference
+            if self._field_signature(arr) == self._delta_x_sig:
+                return self._d_delta_x
+            self._d_delta_x = None
         a = np.asarray(arr)
         if np.iscomplexobj(a):
             a = a.real
         assert a.shape == (self.N,) * 3, "field must have shape (N, N, N)"
         return self._plan.upload_f32(a)
+
+    @staticmethod
+    def _field_signature(a):
+        """Cheap content check of a host field (two BLAS-speed reductions, ~10x cheaper than re-uploading)."""
+        flat = a.reshape(-1)
+        return (float(flat.sum()), float(np.dot(flat, flat)), float(flat[0]), float(flat[-1]))
 
     def _spectrum_arg(self, delta_x, delta_k):
         """Resolve the (delta_x, delta_k, self.delta_k) convention of box.py:241-248."""
@@ -271,8 +287,16 @@ class CosmoBox(object):
             delta_k = self.delta_k
         if isinstance(delta_k, DeviceSpectrum):
             return delta_k
-        # user-supplied full complex cube: keep its Hermitian part's half spectrum
-        a = np.ascontiguousarray(np.asarray(delta_k)[:N // 2 + 1].astype(np.complex64))
+        # user-supplied full complex cube (the spectrum of a real field in every reference call site,
+        # box.py:246,337): its Hermitian projection 1/2 [A(k) + conj A(-k)], planes kx = 0..N/2
+        full = np.asarray(delta_k)
+        if full.shape != (N, N, N):
+            raise ValueError("delta_k must have shape (N, N, N)")
+        h = N // 2 + 1
+        mir = np.concatenate([full[:1], full[:0:-1]], axis=0)[:h]                  # A(-k) on kx = 0..N/2
+        mir = np.concatenate([mir[:, :1], mir[:, :0:-1]], axis=1)
+        mir = np.concatenate([mir[:, :, :1], mir[:, :, :0:-1]], axis=2)
+        a = np.ascontiguousarray((0.5 * (full[:h] + np.conj(mir))).astype(np.complex64))
         return DeviceSpectrum(self, self._plan.upload(a))
 
     # ------------------------------------------------------------- realisations
@@ -307,6 +331,7 @@ class CosmoBox(object):
                       "different redshift than self.redshift.")
             self.delta_x = delta_x
             self._delta_x_host = delta_x
+            self._delta_x_sig = self._field_signature(delta_x)
             self._d_delta_x = field
             self.delta_k = DeviceSpectrum(self, spec)
         return delta_x
@@ -393,8 +418,15 @@ class CosmoBox(object):
 
     # --------------------------------------- redshift space (box.py:384-438)
     def redshift_space_density(self, delta_x=None, velocity_z=None, sigma_nl=0., method='linear'):
+        """
+        Remap the density along z by the peculiar velocity (box.py:384-438).  Only ``method='linear'`` (the
+        reference's default and the only one its examples and tests use) exists on the device; the other
+        ``scipy.interpolate.griddata`` methods the reference would forward (box.py:433-437) are rejected
+        rather than silently run on the host -- this package has no CPU path.
+        """
         if method != 'linear':
-            raise NotImplementedError("only method='linear' is implemented on the GPU path")
+            raise NotImplementedError("redshift_space_density(method=%r): only 'linear' is implemented on the GPU "
+                                      "path (there is no CPU fallback)" % (method,))
         N = self.N
         Hz = 100. * self.cosmo['h'] * ccl.h_over_h0(self.cosmo, self.scale_factor)  # box.py:406
         plan = self._plan

@@ -31,6 +31,10 @@ class Cosmology(dict):
 
     def __init__(self, **kw):
         kw.setdefault("T_CMB", 2.725)
+        tf = kw.get("transfer_function", "eisenstein_hu")
+        if tf not in (None, "eisenstein_hu", "eisenstein_hu_nowiggles"):
+            raise ValueError("built-in cosmology provider: transfer_function=%r is not available (only the "
+                             "Eisenstein-Hu fit); install pyccl for Boltzmann-code spectra" % (tf,))
         super().__init__(**kw)
         self._cache = {}
 
@@ -143,6 +147,9 @@ class _Backend(object):
             setattr(self, fn, getattr(mod, fn))
 
 
+_WARNED = False
+
+
 def get_backend(prefer_ccl=True):
     """Return CCL if importable (as the reference uses), else this module."""
     import sys
@@ -153,4 +160,13 @@ def get_backend(prefer_ccl=True):
                 return _Backend(pyccl, "pyccl")
         except Exception:
             pass
+    global _WARNED
+    if _WARNED:
+        return _Backend(sys.modules[__name__], "builtin-eh98")
+    _WARNED = True
+    import warnings
+    warnings.warn("pyccl is not importable: fastbox_b200 uses its built-in cosmology provider (Eisenstein-Hu 1998 "
+                  "zero-baryon P(k) normalised to sigma8, flat LCDM background).  nonlin_matter_power equals the "
+                  "linear spectrum (no halofit), growth_rate = Omega_m(a)^0.55, and the `transfer_function` keyword "
+                  "only accepts 'eisenstein_hu'.", RuntimeWarning, stacklevel=2)
     return _Backend(sys.modules[__name__], "builtin-eh98")

@@ -137,6 +137,11 @@ int pk_fetch(fb_plan* p, fb_pk_result* out) {
     double* ds = reinterpret_cast<double*>(dc + (FB_MAX_EDGES + 1));
     k_pk_fold<<<n, 32, 0, p->stream>>>(p->h_count, p->h_sums, dc, ds);
     FB_LAUNCH_CHECK();
+    return pk_fetch_folded(p, out);
+}
+
+int pk_fetch_folded(fb_plan* p, fb_pk_result* out) {
+    const int n = p->nedges + 1;
     const size_t bytes = 5 * (size_t)(FB_MAX_EDGES + 1) * 8;
     FB_CUDA(cudaMemcpyAsync(p->pk_host, p->pk_fold, bytes, cudaMemcpyDeviceToHost, p->stream));
     FB_CUDA(cudaStreamSynchronize(p->stream));
@@ -151,11 +156,11 @@ int pk_fetch(fb_plan* p, fb_pk_result* out) {
     return 0;
 }
 
-static int scal_clear(fb_plan* p) {
+int scal_clear(fb_plan* p) {
     FB_CUDA(cudaMemsetAsync(p->scal, 0, 8 * sizeof(double), p->stream));
     return 0;
 }
-static int scal_fetch(fb_plan* p, double* out, int n) {
+int scal_fetch(fb_plan* p, double* out, int n) {
     if (!out) return 0;
     FB_CUDA(cudaMemcpyAsync(p->scal_host, p->scal, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     FB_CUDA(cudaStreamSynchronize(p->stream));
@@ -209,6 +214,15 @@ fb::PkDev fb_plan::pkdev() const {
     d.l2 = h_sums + 2 * (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
     d.l4 = h_sums + 3 * (size_t)FB_PK_COPIES * (FB_MAX_EDGES + 1);
     return d;
+}
+
+int fb::check_flags(fb_plan* p, int flags) {
+    if (flags & FB_F_SQRTPK) FB_CHECK(p->sqrtp != nullptr, "FB_F_SQRTPK set but no sqrt(P) table (fb_set_sqrt_pk)");
+    if (flags & FB_F_FILTER)
+        FB_CHECK(p->tdense != nullptr || (p->tperp != nullptr && p->tpar != nullptr),
+                 "FB_F_FILTER set but no filter table (fb_set_filter)");
+    if (flags & FB_F_PK) FB_CHECK(p->nedges > 0, "FB_F_PK set but no bins (fb_set_pk_bins)");
+    return 0;
 }
 
 extern "C" {
@@ -288,6 +302,7 @@ int fb_plan_destroy(fb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
+    fb::dist_destroy(p);
     cudaFree(p->tw);
     cudaFree(p->ax);
     cudaFree(p->thr);
@@ -330,6 +345,11 @@ int fb_dev_alloc(void** ptr, size_t bytes) {
     FB_CUDA(cudaMalloc(ptr, bytes));
     return 0;
 }
+int fb_dev_alloc_on(int device, void** ptr, size_t bytes) {
+    FB_CUDA(cudaSetDevice(device));
+    FB_CUDA(cudaMalloc(ptr, bytes));
+    return 0;
+}
 int fb_dev_free(void* ptr) {
     FB_CUDA(cudaFree(ptr));
     return 0;
@@ -343,6 +363,7 @@ int fb_host_free(void* ptr) {
     return 0;
 }
 int fb_copy(fb_plan* p, void* dst, const void* src, size_t bytes) {
+    FB_CUDA(cudaSetDevice(p->device));
     FB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, p->stream));
     FB_CUDA(cudaStreamSynchronize(p->stream));
     return 0;
@@ -446,15 +467,6 @@ int fb_set_pk_bins(fb_plan* p, const double* thresholds, int nedges) {
             p->bin_inv_d = 1.0 / d;
         }
     }
-    return 0;
-}
-
-static int check_flags(fb_plan* p, int flags) {
-    if (flags & FB_F_SQRTPK) FB_CHECK(p->sqrtp != nullptr, "FB_F_SQRTPK set but no sqrt(P) table (fb_set_sqrt_pk)");
-    if (flags & FB_F_FILTER)
-        FB_CHECK(p->tdense != nullptr || (p->tperp != nullptr && p->tpar != nullptr),
-                 "FB_F_FILTER set but no filter table (fb_set_filter)");
-    if (flags & FB_F_PK) FB_CHECK(p->nedges > 0, "FB_F_PK set but no bins (fb_set_pk_bins)");
     return 0;
 }
 

@@ -9,40 +9,35 @@ int env_int(const char* name, int dflt) {
     return s && *s ? atoi(s) : dflt;
 }
 
+SlabView plain_view(float2* base) {
+    SlabView v;
+    memset(&v, 0, sizeof(v));
+    v.base[0] = base;
+    return v;
+}
+
+// [d][plane][y'][z] blocks of one local buffer (what an NCCL all-to-all sends / receives)
+SlabView block_view(float2* base, int ny, int nplanes, int N) {
+    SlabView v = plain_view(base);
+    if (ny > 0) {
+        v.ny = ny;
+        v.ny_shift = 0;
+        while ((1 << v.ny_shift) < ny) ++v.ny_shift;
+        for (int d = 0; d < N / ny && d < FB_MAX_RANKS; ++d) v.base[d] = base + (size_t)d * nplanes * ny * N;
+    }
+    return v;
+}
+
 template <int N, int CZ>
-static int launch_cols_t(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign) {
+static int launch_cols_t(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st) {
     using G = ColGeom<N, CZ>;
     dim3 grid(N / CZ, nplanes);
-    const bool slab = in_ny != 0 || out_ny != 0;
-    if constexpr (N >= 256) {
-        // persistent cp.async-pipelined kernel (two tile buffers).  Measured SLOWER than the plain kernel on
-        // B200 (2.25 ms vs 1.76 ms at 1024^3: 8-byte LDGSTS issue rate + one resident CTA), so it is
-        // opt-in (FB_COLS_PIPE=1) and kept as the starting point for a TMA-tiled version.
-        if (!slab && 2 * G::SMEM <= 220 * 1024 && env_int("FB_COLS_PIPE", 0)) {
-            const int ntiles = (N / CZ) * nplanes;
-            int per_sm = (int)((220 * 1024) / (2 * G::SMEM + 1024));
-            per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-            per_sm = env_int("FB_PIPE_CTAS", per_sm);
-            const int want = p->sm_count * per_sm;
-            const int ctas = want < ntiles ? want : ntiles;
-            if (sign < 0) {
-                auto kern = k_cols_c2c_pipe<N, CZ, -1>;
-                if (set_smem(kern, 2 * G::SMEM)) return -2;
-                kern<<<ctas, G::THREADS, 2 * G::SMEM, p->stream>>>(in, out, ntiles, p->tw);
-            } else {
-                auto kern = k_cols_c2c_pipe<N, CZ, +1>;
-                if (set_smem(kern, 2 * G::SMEM)) return -2;
-                kern<<<ctas, G::THREADS, 2 * G::SMEM, p->stream>>>(in, out, ntiles, p->tw);
-            }
-            FB_LAUNCH_CHECK();
-            return 0;
-        }
-    }
+    const bool slab = vin.ny != 0 || vout.ny != 0;
 #define FB_COLS_LAUNCH(SIGN_, SLAB_)                                                         \
     {                                                                                        \
         auto kern = k_cols_c2c<N, CZ, SIGN_, SLAB_>;                                         \
         if (set_smem(kern, G::SMEM)) return -2;                                              \
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(in, out, in_ny, out_ny, p->tw);       \
+        kern<<<grid, G::THREADS, G::SMEM, st>>>(vin.base[0], vout.base[0], vin, vout, p->tw); \
     }
     if (sign < 0) {
         if (slab) FB_COLS_LAUNCH(-1, true) else FB_COLS_LAUNCH(-1, false)
@@ -56,34 +51,43 @@ static int launch_cols_t(fb_plan* p, const float2* in, float2* out, int in_ny, i
 
 // tile width (columns per CTA).  HBM3e on B200 sustains full bandwidth down to 32-byte row
 // chunks (tools/probe.py), so narrow tiles are preferred: more CTAs per SM overlap load /
-// exchange / store phases.  FB_CZ_COLS / FB_CZ_X override for tuning.
+// exchange / store phases.  FB_CZ_COLS overrides for tuning; `cz_hint` > 0 is the caller's choice
+// (the peer-store exchange prefers 64-byte rows on NVLink).
 template <int N>
-static int launch_cols_n(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign, int dflt) {
-    const int cz = env_int("FB_CZ_COLS", dflt);
-    if (cz == 4) return launch_cols_t<N, 4>(p, in, out, in_ny, out_ny, nplanes, sign);
-    if (cz == 8) return launch_cols_t<N, 8>(p, in, out, in_ny, out_ny, nplanes, sign);
+static int launch_cols_n(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st,
+                         int dflt, int cz_hint) {
+    const int cz = cz_hint > 0 ? cz_hint : env_int("FB_CZ_COLS", dflt);
+    if (cz == 4) return launch_cols_t<N, 4>(p, vin, vout, nplanes, sign, st);
+    if (cz == 8) return launch_cols_t<N, 8>(p, vin, vout, nplanes, sign, st);
     if constexpr (N <= 1024) {
-        if (cz == 16) return launch_cols_t<N, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
+        if (cz == 16) return launch_cols_t<N, 16>(p, vin, vout, nplanes, sign, st);
     }
-    set_error("FB_CZ_COLS=%d not available for N=%d", cz, N);
+    set_error("y pass: %d columns per CTA not available for N=%d", cz, N);
     return -1;
+}
+
+int launch_cols_views(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st,
+                      int cz_hint) {
+    if (nplanes <= 0) return 0;
+    switch (p->N) {
+        case 8: return launch_cols_t<8, 8>(p, vin, vout, nplanes, sign, st);
+        case 16: return launch_cols_t<16, 16>(p, vin, vout, nplanes, sign, st);
+        case 32: return launch_cols_t<32, 16>(p, vin, vout, nplanes, sign, st);
+        case 64: return launch_cols_t<64, 16>(p, vin, vout, nplanes, sign, st);
+        case 128: return launch_cols_t<128, 16>(p, vin, vout, nplanes, sign, st);
+        case 256: return launch_cols_n<256>(p, vin, vout, nplanes, sign, st, 16, cz_hint);
+        case 512: return launch_cols_n<512>(p, vin, vout, nplanes, sign, st, 8, cz_hint);
+        case 1024: return launch_cols_n<1024>(p, vin, vout, nplanes, sign, st, 8, cz_hint);
+        case 2048: return launch_cols_n<2048>(p, vin, vout, nplanes, sign, st, 4, cz_hint);
+        default: set_error("unsupported N=%d", p->N); return -1;
+    }
 }
 
 int launch_cols(fb_plan* p, float2* data, int nplanes, int sign) { return launch_cols_ex(p, data, data, 0, 0, nplanes, sign); }
 
 int launch_cols_ex(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign) {
-    switch (p->N) {
-        case 8: return launch_cols_t<8, 8>(p, in, out, in_ny, out_ny, nplanes, sign);
-        case 16: return launch_cols_t<16, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
-        case 32: return launch_cols_t<32, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
-        case 64: return launch_cols_t<64, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
-        case 128: return launch_cols_t<128, 16>(p, in, out, in_ny, out_ny, nplanes, sign);
-        case 256: return launch_cols_n<256>(p, in, out, in_ny, out_ny, nplanes, sign, 16);
-        case 512: return launch_cols_n<512>(p, in, out, in_ny, out_ny, nplanes, sign, 8);
-        case 1024: return launch_cols_n<1024>(p, in, out, in_ny, out_ny, nplanes, sign, 8);
-        case 2048: return launch_cols_n<2048>(p, in, out, in_ny, out_ny, nplanes, sign, 4);
-        default: set_error("unsupported N=%d", p->N); return -1;
-    }
+    return launch_cols_views(p, block_view(const_cast<float2*>(in), in_ny, nplanes, p->N),
+                             block_view(out, out_ny, nplanes, p->N), nplanes, sign, p->stream, 0);
 }
 
 template <int N, int CZ>

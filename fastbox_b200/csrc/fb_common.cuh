@@ -125,6 +125,7 @@ struct fb_plan {
     cudaEvent_t ev[8];
     float last_ms[8];
     int n_last;
+    struct fb_dist_state* dist;     // multi-GPU exchange state (fb_dist.cu), NULL until fb_dist_init
     fb::KSpace kspace() const;
     fb::PkDev pkdev() const;
 };
@@ -141,6 +142,11 @@ int stage_out_end(fb_plan* p, int slot, void* ptr, size_t bytes);
 bool is_device_ptr(const void* ptr);
 int pk_clear(fb_plan* p);
 int pk_fetch(fb_plan* p, fb_pk_result* out);
+int pk_fetch_folded(fb_plan* p, fb_pk_result* out);     // D2H of p->pk_fold only (already folded / reduced)
+int scal_clear(fb_plan* p);
+int scal_fetch(fb_plan* p, double* out, int n);
+int check_flags(fb_plan* p, int flags);
+void dist_destroy(fb_plan* p);
 
 __device__ __forceinline__ int mode_number(int i, int N) { return i < N / 2 ? i : i - N; }   // box.py:119
 

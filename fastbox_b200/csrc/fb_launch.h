@@ -12,6 +12,10 @@ int launch_rows_fwd(fb_plan* p, const RowsArgs& a);
 int launch_pk_spectrum(fb_plan* p, const float2* spec, const float2* cross, int nplanes, int full_cube, int flags);
 int launch_cols(fb_plan* p, float2* data, int nplanes, int sign);
 int launch_cols_ex(fb_plan* p, const float2* in, float2* out, int in_ny, int out_ny, int nplanes, int sign);
+SlabView plain_view(float2* base);
+SlabView block_view(float2* base, int ny, int nplanes, int N);
+int launch_cols_views(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st,
+                      int cz_hint);
 int launch_x_c2r(fb_plan* p, const XArgs& a);
 int launch_x_r2c(fb_plan* p, const XArgs& a);
 

@@ -379,6 +379,28 @@ int fb_convert_f32_to_f64(fb_plan* p, const float* src, double* dst, size_t n) {
     return 0;
 }
 
+// out = counts * mul + add  (halo overdensity N_h / N_bar - 1 for the cross spectrum, example_halos.py:46-53)
+__global__ void __launch_bounds__(256) k_counts_to_field(const int32_t* __restrict__ c, float* __restrict__ out, size_t n,
+                                                          float mul, float add) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n / 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(c) + q);
+        reinterpret_cast<float4*>(out)[q] = make_float4(fmaf((float)v.x, mul, add), fmaf((float)v.y, mul, add),
+                                                        fmaf((float)v.z, mul, add), fmaf((float)v.w, mul, add));
+    }
+    for (size_t j = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        out[j] = fmaf((float)c[j], mul, add);
+}
+
+int fb_counts_to_field(fb_plan* p, const int32_t* counts, size_t n, float mul, float add, float* out) {
+    FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(is_device_ptr(counts) && is_device_ptr(out), "fb_counts_to_field: buffers must be device memory");
+    k_counts_to_field<<<grid_for(n / 4 + 1, 256, p->sm_count), 256, 0, p->stream>>>(counts, out, n, mul, add);
+    FB_LAUNCH_CHECK();
+    return 0;
+}
+
 int fb_rsd_remap(fb_plan* p, const float* delta, const float* vel_z, const float* vel_nl, const double* zgrid,
                  double Hz, float* out) {
     FB_CUDA(cudaSetDevice(p->device));

@@ -7,7 +7,6 @@
 //     xc2r  (a -> x, stride = plane size; half-length complex FFT + real pre-processing)
 // Forward (P(k)) order is the mirror image: xr2c, cols, rows (+ histogram epilogue).
 #pragma once
-#include <cuda_pipeline.h>
 #include "fb_kspace.cuh"
 
 namespace fb {
@@ -753,30 +752,40 @@ struct ColGeom {
 };
 
 // Slab-decomposed runs exchange the y axis between ranks right after (inverse) / before
-// (forward) this pass.  With ny > 0 the y index is split as y = d*ny + y' and the element lives
-// at [d][plane][y'][z]: the block for destination rank d is contiguous, so the all-to-all needs
-// no pack / unpack pass over HBM.  ny = 0 is the plain [plane][y][z] layout.
-__device__ __forceinline__ size_t col_index(int plane, int nplanes, int y, int ny, int N) {
-    if (ny == 0) return ((size_t)plane * N + y) * N;
-    const int d = y / ny, yy = y - d * ny;
-    return (((size_t)d * nplanes + plane) * ny + yy) * N;
+// (forward) this pass.  A SlabView splits the y index as y = d*ny + y' and places element
+// (plane, y, z) at base[d] + (plane*ny + y')*N + z: one base pointer per rank d.  The bases may be
+//   * blocks of one local buffer laid out [d][plane][y'][z] (contiguous per peer: an NCCL all-to-all
+//     needs no pack / unpack pass), or
+//   * the receive buffers of the PEER GPUs themselves, mapped over NVLink (fb_dist.cu): the stores of
+//     the y pass are then the exchange -- compute and "collective" are one kernel.
+// ny = 0 is the plain local [plane][y][z] layout at base[0].
+#define FB_MAX_RANKS 8
+struct SlabView {
+    float2* base[FB_MAX_RANKS];
+    int ny, ny_shift;
+};
+__device__ __forceinline__ float2* slab_ptr(const SlabView& v, int plane, int y, int N) {
+    if (v.ny == 0) return v.base[0] + ((size_t)plane * N + y) * N;
+    const int d = y >> v.ny_shift, yy = y & (v.ny - 1);
+    return v.base[d] + ((size_t)plane * v.ny + yy) * N;
 }
 
 template <int N, int CZ, int S, bool SLAB>
 __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const float2* __restrict__ in,
-                                                                     float2* __restrict__ out, int in_ny, int out_ny,
+                                                                     float2* __restrict__ out, const SlabView vin,
+                                                                     const SlabView vout,
                                                                      const float2* __restrict__ tw) {
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
-    const int plane = blockIdx.y, nplanes = gridDim.y;
+    const int plane = blockIdx.y;
     const size_t zc = (size_t)blockIdx.x * CZ + col;
     float2 v[P];
     if constexpr (SLAB) {
 #pragma unroll
-        for (int q = 0; q < P; ++q) v[q] = in[col_index(plane, nplanes, t + T * q, in_ny, N) + zc];
+        for (int q = 0; q < P; ++q) v[q] = slab_ptr(vin, plane, t + T * q, N)[zc];
     } else {
         const float2* p = in + ((size_t)plane * N + t) * N + zc;     // one 64-bit base, 32-bit constant offsets
 #pragma unroll
@@ -786,63 +795,11 @@ __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const floa
     fft_regs<N, P, C::R1, C::R2, C::R3, S>(v, t, sm, sl, tw);
     if constexpr (SLAB) {
 #pragma unroll
-        for (int q = 0; q < P; ++q) out[col_index(plane, nplanes, t + T * q, out_ny, N) + zc] = v[q];
+        for (int q = 0; q < P; ++q) slab_ptr(vout, plane, t + T * q, N)[zc] = v[q];
     } else {
         float2* p = out + ((size_t)plane * N + t) * N + zc;
 #pragma unroll
         for (int q = 0; q < P; ++q) p[(unsigned)(T * q) * (unsigned)N] = v[q];
-    }
-}
-
-// Persistent, software-pipelined variant of the y pass (plain layout): one CTA per SM loops over
-// tiles; while tile i is transformed, tile i+1 streams into the other shared-memory buffer with
-// cp.async (LDGSTS), so HBM never idles during the compute / exchange phases.  The landed tile is
-// transformed in place (its buffer doubles as the exchange buffer).
-template <int N, int CZ, int S>
-__global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS, (ColGeom<N, CZ>::THREADS <= 256 ? 3 : 1)) k_cols_c2c_pipe(const float2* __restrict__ in,
-                                                                             float2* __restrict__ out, int ntiles,
-                                                                             const float2* __restrict__ tw) {
-    using C = FftCfg<N>;
-    constexpr int P = C::P, T = C::T;
-    constexpr int TILE = (N + N / 16) * CZ;              // float2 elements per buffer
-    constexpr int PS = ColLayout<CZ>::pstride(T);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* sm = reinterpret_cast<float2*>(smem_raw);
-    const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
-    ColLayout<CZ> sl{col};
-    const int p0 = sl(t);
-    constexpr int TPP = N / CZ;                          // tiles per plane
-    auto tile_ptr = [&](int tile) -> size_t {
-        const int plane = tile / TPP, zt = tile - plane * TPP;
-        return ((size_t)plane * N + t) * N + (size_t)zt * CZ + col;
-    };
-    auto prefetch = [&](int tile, float2* buf) {
-        const float2* g = in + tile_ptr(tile);
-#pragma unroll
-        for (int q = 0; q < P; ++q) __pipeline_memcpy_async(buf + p0 + q * PS, g + (size_t)(T * q) * N, sizeof(float2));
-        __pipeline_commit();
-    };
-    int tile = blockIdx.x;
-    int cur = 0;
-    if (tile < ntiles) prefetch(tile, sm);
-    for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
-        float2* buf = sm + cur * TILE;
-        const int next = tile + gridDim.x;
-        if (next < ntiles) {
-            prefetch(next, sm + (cur ^ 1) * TILE);
-            __pipeline_wait_prior(1);
-        } else {
-            __pipeline_wait_prior(0);
-        }
-        float2 v[P];
-#pragma unroll
-        for (int q = 0; q < P; ++q) v[q] = buf[p0 + q * PS];      // own copies: visible after the wait
-        __syncthreads();                                           // everyone has its inputs before in-place exchanges
-        fft_regs<N, P, C::R1, C::R2, C::R3, S>(v, t, buf, sl, tw);
-        float2* g = out + tile_ptr(tile);
-#pragma unroll
-        for (int q = 0; q < P; ++q) g[(size_t)(T * q) * N] = v[q];
-        __syncthreads();                                           // buffer free before it is refilled
     }
 }
 
@@ -866,6 +823,11 @@ struct XArgs {
     int flags;
     float scale;
     double* sums;           // [0] sum, [1] sum of squares
+    // x r2c of a slab-decomposed run: plane k of the result belongs to rank d = min(k >> per_shift, nranks-1)
+    // and is stored at peer_out[d] + (k - (d << per_shift)) * ncols (the peer's receive buffer, mapped over
+    // NVLink); nranks = 0: everything goes to spec_out
+    float2* peer_out[FB_MAX_RANKS];
+    int nranks, per_shift;
 };
 
 template <int N, int CZ>
@@ -987,7 +949,11 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     __syncthreads();
     fft_store_natural<M, P>(v, t, sm, sl);
     __syncthreads();
-    float2* dst = A.spec_out + g;
+    auto plane_ptr = [&](int k) -> float2* {
+        if (A.nranks == 0) return A.spec_out + (size_t)k * A.ncols + g;
+        const int d = min(k >> A.per_shift, A.nranks - 1);
+        return A.peer_out[d] + (size_t)(k - (d << A.per_shift)) * A.ncols + g;
+    };
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
@@ -996,8 +962,8 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
         const float2 w = FB_TW(A.tw, N, k);      // e^{-2 pi i k / N}
         const float2 sp = cadd(zk, zm), df = cmul(csub(zk, zm), w);
         // 1/2 (sp - i df)
-        dst[(size_t)k * A.ncols] = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));
-        if (k == 0) dst[(size_t)M * A.ncols] = make_float2(zk.x - zk.y, 0.f);
+        *plane_ptr(k) = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));
+        if (k == 0) *plane_ptr(M) = make_float2(zk.x - zk.y, 0.f);
     }
 }
 

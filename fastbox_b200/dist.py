@@ -16,9 +16,19 @@ kernels are needed.  P(k) moments are per-rank partial histograms summed with ``
 
 The reference (``fastbox/box.py``) is single process; this module has no counterpart there.
 
-The local compute is behind ``engine`` so that the exchange bookkeeping can be exercised on
-CPU (gloo) with a NumPy engine in ``tests/test_dist_gloo.py``; the product engine is
-``CudaEngine`` (C ABI, no CPU fallback).
+Two exchange mechanisms exist:
+
+* ``NvlinkRealiser`` (default): the exchange lives INSIDE the C library (``csrc/fb_dist.cu``).  Every rank
+  maps the receive buffers of its peers (CUDA IPC over NVLink) and the y pass stores each element straight
+  into the buffer of the rank that owns it -- transform pass and all-to-all are one kernel; the P(k) moments
+  are summed through per-rank slots and the ranks meet at device-side epoch flags.  ``torch.distributed`` is
+  used once, at set-up, to publish the 128-byte handles.
+* ``DistributedRealiser`` + ``CudaEngine``: the same passes with ``all_to_all_single`` (NCCL) between them;
+  kept as the comparison point and for clusters where peer mapping is not available.
+
+The local compute of the NCCL variant is behind ``engine`` so that the exchange bookkeeping can be exercised
+on CPU (gloo) with a NumPy engine in ``tests/test_dist_gloo.py``; the product engines are C ABI only (no CPU
+fallback).
 """
 import numpy as np
 
@@ -257,3 +267,54 @@ class DistributedRealiser(object):
         sums = e.x_to_real(flags=flags & _lib.F_EXP, scale=scale)
         pk = self._reduce_moments(res) if want_pk else None
         return e.field, pk, sums
+
+
+def gather_handles(blob, world, group=None):
+    """All ranks' ``fb_dist_get_handle`` blobs in rank order ((world, 128) uint8), via torch.distributed."""
+    if world == 1:
+        return np.ascontiguousarray(blob).reshape(1, -1)
+    import torch
+    import torch.distributed as dist
+    on_gpu = dist.get_backend(group) == "nccl"
+    t = torch.from_numpy(np.ascontiguousarray(blob))
+    if on_gpu:
+        t = t.cuda()
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return np.stack([o.cpu().numpy() for o in out])
+
+
+class NvlinkRealiser(object):
+    """
+    Slab-decomposed realise (+ filter + P(k)) and forward P(k) with the exchange inside the library
+    (``fb_dist_*``, peer stores over NVLink).  One instance per process / GPU; every method is collective.
+    """
+
+    def __init__(self, N, L, rank, world, device, group=None, with_forward=True, chunks=4):
+        self.N, self.rank, self.world, self.chunks = N, rank, world, chunks
+        self.plan = _lib.Plan(N, L[0], L[1], L[2], device)
+        self.plan.dist_init(rank, world, with_forward)
+        self.plan.dist_connect(gather_handles(self.plan.dist_handle(), world, group))
+        info = self.plan.dist_info()
+        self.a0, self.na, self.y0, self.ny = info["a0"], info["na"], info["y0"], info["ny"]
+        self.block_bytes = info["block_bytes"]
+        self.field = self.plan.alloc(N * self.ny * N * 4)              # float32 [N][ny][N]
+        self.plan.dist_barrier()                                       # every rank has mapped every block
+
+    def realise(self, seed, flags, want_pk=False, scale=1.0, want_sums=False):
+        """Returns (device field slab [N][ny][N], global P(k) moments or None, local (sum, sum of squares))."""
+        res, sums = self.plan.dist_realise(seed, flags, self.field, scale=scale, chunks=self.chunks,
+                                           want_pk=want_pk, want_sums=want_sums)
+        return self.field, res, sums
+
+    def power_spectrum(self, field=None, poles=False):
+        """Global binned P(k) moments of the sharded real field (default: the last realised one)."""
+        res = self.plan.dist_power_spectrum(self.field if field is None else field, poles=poles)
+        res.pop("_st", None)
+        return res
+
+    def field_host(self):
+        return self.plan.download(self.field, (self.N, self.ny, self.N), np.float32)
+
+    def close(self):
+        self.plan.close()

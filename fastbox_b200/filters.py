@@ -12,13 +12,13 @@ from . import _lib
 _plans = {}
 
 
-def _plan_for(N):
-    if N not in _plans:
-        _plans[N] = _lib.Plan(N, 1.0, 1.0, 1.0)
-    return _plans[N]
+def _plan_for(N, device=0):
+    if (N, device) not in _plans:
+        _plans[(N, device)] = _lib.Plan(N, 1.0, 1.0, 1.0, device)
+    return _plans[(N, device)]
 
 
-def mean_spectrum_filter(field, return_mean=False):
+def mean_spectrum_filter(field, return_mean=False, device=0):
     """
     Subtract the mean from each frequency slice (filters.py:35-55); the 3rd axis is frequency.
     ``field`` must be a cube (N, N, N) with N a power of two in [8, 2048].  Returns float64 like
@@ -28,7 +28,7 @@ def mean_spectrum_filter(field, return_mean=False):
     if field.ndim != 3 or not (field.shape[0] == field.shape[1] == field.shape[2]):
         raise ValueError("mean_spectrum_filter: field must have shape (N, N, N)")
     N = field.shape[0]
-    plan = _plan_for(N)
+    plan = _plan_for(N, device)
     d_in = plan.upload_f32(field)
     d_out = plan.alloc(N ** 3 * 4)
     mean = plan.mean_spectrum_filter(d_in, d_out)
@@ -36,7 +36,7 @@ def mean_spectrum_filter(field, return_mean=False):
     return (out, mean) if return_mean else out
 
 
-def pca_filter(field, nmodes, fit_powerlaw=False, return_filter=False):
+def pca_filter(field, nmodes, fit_powerlaw=False, return_filter=False, device=0):
     """
     PCA foreground filter (filters.py:93-183): subtract the ``nmodes`` leading eigenmodes of the
     frequency-frequency covariance (plus the mean spectrum) from every line of sight.
@@ -54,7 +54,7 @@ def pca_filter(field, nmodes, fit_powerlaw=False, return_filter=False):
     nmodes = int(nmodes)
     if not 1 <= nmodes <= min(32, N):
         raise ValueError("pca_filter: nmodes must be in [1, 32]")
-    plan = _plan_for(N)
+    plan = _plan_for(N, device)
     d_cube = plan.upload(np.ascontiguousarray(field))
     d_mean, cov = plan.pca_covariance(d_cube)
     if fit_powerlaw:

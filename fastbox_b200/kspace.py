@@ -222,11 +222,15 @@ def filter_tables(transfer_fn, N, Lx, Ly, Lz, nprobe=4096, rtol=1e-10, force_den
     kperp = TWO_PI * np.sqrt((m[:h, None] / Lx) ** 2. + (m[None, :] / Ly) ** 2.)     # (h, N)
     kpar = TWO_PI * m / Lz                                                           # (N,)
     with np.errstate(all="ignore"):
+        rng = np.random.RandomState(12345)
+        ia, ib, ic = rng.randint(0, h, nprobe), rng.randint(0, N, nprobe), rng.randint(0, N, nprobe)
+        raw = np.asarray(transfer_fn(kperp[ia, ib], kpar[ic]))
+        if np.iscomplexobj(raw) and np.any(np.nan_to_num(raw.imag) != 0.0):
+            raise ValueError("transfer_fn returned complex values: only real transfer functions are supported on "
+                             "the GPU path (the tables are real multipliers)")
         if not force_dense:
             # reference point with a non-zero value
-            rng = np.random.RandomState(12345)
-            ia, ib, ic = rng.randint(0, h, nprobe), rng.randint(0, N, nprobe), rng.randint(0, N, nprobe)
-            probe = np.nan_to_num(np.asarray(transfer_fn(kperp[ia, ib], kpar[ic]), dtype=np.float64))
+            probe = np.nan_to_num(np.asarray(raw.real if np.iscomplexobj(raw) else raw, dtype=np.float64))
             j = int(np.argmax(np.abs(probe)))
             t00 = probe[j]
             if t00 != 0.0:

@@ -84,7 +84,8 @@ uint64_t fb_launch_count(void);
 int fb_plan_set_slab(fb_plan* plan, int a0, int na, int y0, int ny);
 
 /* ---- memory helpers (the shim keeps fields device resident between calls) - */
-int fb_dev_alloc(void** ptr, size_t bytes);
+int fb_dev_alloc(void** ptr, size_t bytes);            /* on the current device */
+int fb_dev_alloc_on(int device, void** ptr, size_t bytes);   /* on a named device (a plan's) */
 int fb_dev_free(void* ptr);
 int fb_host_alloc(void** ptr, size_t bytes);        /* pinned */
 int fb_host_free(void* ptr);
@@ -160,6 +161,10 @@ int fb_halo_counts(fb_plan* plan, const float* delta, const float* nbar, int nba
                    int bias_kind, int lognormal, double mean_exp, const double* uniforms, int32_t* counts_out,
                    float* mean_out);
 
+/* out = counts * mul + add (float32): the halo overdensity N_h / N_bar - 1 fed to the cross spectrum,
+ * examples/example_halos.py:46-53.  Device buffers.                                                */
+int fb_counts_to_field(fb_plan* plan, const int32_t* counts, size_t n, float mul, float add, float* out);
+
 /* ---- halo catalogue: halos.py:120-176 ------------------------------------------ */
 /* counts[N^3] (int32, >= 0, < 1024) -> cat[nhalo][3] float64 comoving positions in the reference's order
  * (ascending count value, then C-order voxel index, each voxel repeated `count` times).
@@ -222,6 +227,33 @@ int fb_realise_local_kspace(fb_plan* plan, uint64_t seed, int flags, void* work,
  * y columns + z rows on the local kx planes, optional spectrum store and binned moments.      */
 int fb_forward_local_kspace(fb_plan* plan, const void* recv, void* work, int ny, void* spec_out, int flags,
                             fb_pk_result* pk);
+/* ---- multi-GPU pipelines with the exchange inside the library (fb_dist.cu) ------------------------
+ * One process per GPU.  Every rank calls fb_dist_init (sets the slab of `rank` out of `world`: kx planes
+ * [rank*N/2/world, ...) -- the last rank also owns the Nyquist plane -- and y rows [rank*N/world, ...);
+ * allocates the exchange block), publishes the FB_DIST_HANDLE_BYTES blob of fb_dist_get_handle to all ranks
+ * by any means (fastbox_b200/dist.py: one torch.distributed all_gather at set-up) and passes the `world`
+ * blobs in rank order to fb_dist_connect, which maps the peers' blocks (CUDA IPC over NVLink).  From then on
+ * the transposes of the 3-D transforms are the STORES of the FFT pass before them, straight into the peer's
+ * receive buffer; P(k) moments are summed through per-rank slots; ranks meet at device-side epoch flags.
+ * No NCCL call is on the data path.  All calls are collective (same order on every rank).              */
+#define FB_DIST_HANDLE_BYTES 128
+int fb_dist_init(fb_plan* plan, int rank, int world, int with_forward);
+int fb_dist_get_handle(fb_plan* plan, void* handle_out);
+int fb_dist_connect(fb_plan* plan, const void* handles);
+int fb_dist_info(fb_plan* plan, int* rank, int* world, int* a0, int* na, int* y0, int* ny, size_t* block_bytes);
+int fb_dist_barrier(fb_plan* plan);
+/* realise (+ filter + P(k)) of box.py:161-193 on this rank's slab, Philox noise keyed by the global cell
+ * index (any GPU count gives the same field).  field_out: DEVICE float32 [N][ny][N]; pk: moments summed over
+ * all ranks (nullable); sums_out[2]: local sum / sum of squares (nullable).  `chunks` first-pass chunks
+ * overlap the peer stores of the y pass.  phase 0 = whole step; 1 = up to the signal; 2 = from the wait.  */
+int fb_dist_realise(fb_plan* plan, uint64_t seed, int flags, float scale, int chunks, int phase, float* field_out,
+                    fb_pk_result* pk, double* sums_out);
+/* the exchange alone (y pass storing into the peers + barrier), average ms per iteration: NVLink roofline */
+int fb_dist_bench_exchange(fb_plan* plan, int iters, float* ms_out);
+/* binned P(k) of the sharded real field (box.py:736-764); field: DEVICE float32 [N][ny][N].
+ * phase 0 = all; 1 = x pass + signal; 2 = wait + k-space passes + signal; 3 = wait + sum.               */
+int fb_dist_power_spectrum(fb_plan* plan, const float* field, int flags, int phase, fb_pk_result* pk);
+
 /* strided HBM copy micro-benchmark: rows of `chunk_bytes`, returns GB/s        */
 int fb_bench_strided_copy(fb_plan* plan, size_t total_bytes, int chunk_bytes, int iters, double* gbs);
 /* CUDA-event stopwatch on the plan's stream (bench.py times the step loop with it) */

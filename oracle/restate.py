@@ -161,6 +161,128 @@ def realise_density_lean(re, im, pk_of_k, N, Lx, Ly, Lz):
 
 
 # --------------------------------------------------------------------------
+# Slab-wise restatement for sizes the ports above cannot hold (512^3 .. 1024^3):
+# same arithmetic as ``realise_density_lean`` + ``binned_power_spectrum_lean``
+# (both pinned bit-for-bit to the reference at small N; this function is checked
+# against them in tests/test_oracle_cpu.py), one kx plane at a time, float64.
+# --------------------------------------------------------------------------
+def k_plane(a, N, Lx, Ly, Lz):
+    """|k| on the plane kx index ``a`` with the operation order of box.py:125-127."""
+    m = mode_numbers(N).astype(np.float64)
+    return TWO_PI * np.sqrt((m[a] / Lx) ** 2. + (m[:, None] / Ly) ** 2. + (m[None, :] / Lz) ** 2.)
+
+
+def _mirror2(p):
+    p = np.concatenate([p[:1], p[:0:-1]], axis=0)
+    return np.concatenate([p[:, :1], p[:, :0:-1]], axis=1)
+
+
+def hermitian_plane(re_a, im_a, re_m, im_m):
+    """One kx plane of ``hermitian_half_from_noise`` (amp = 1): re_m, im_m are the noise planes (-a) % N."""
+    return 0.5 * (re_a + _mirror2(re_m)) + 0.5j * (im_a - _mirror2(im_m))
+
+
+def kspace_factor_plane(kind, a, N, Lx, Ly, Lz):
+    """Per-mode factor of box.py:254-274 (velocity components, without `fac`) / box.py:347-348 (potential)."""
+    m = mode_numbers(N).astype(np.float64)
+    k2 = k_plane(a, N, Lx, Ly, Lz) ** 2.
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if kind == "potential":
+            f = 1.0 / k2
+            if a == 0:
+                f[0, 0] = 0.
+            return f
+        ax = {"vel_x": 0, "vel_y": 1, "vel_z": 2}[kind]
+        K = [np.full((1, 1), m[a]), m[:, None], m[None, :]][ax]
+        L = (Lx, Ly, Lz)[ax]
+        f = np.nan_to_num(1.j * K * (TWO_PI / L) / k2)
+    if ax == 0 and a == N // 2:                                  # box.py:268-274
+        f[:] = 0.
+    elif ax == 1:
+        f[N // 2, :] = 0.
+    elif ax == 2:
+        f[:, N // 2] = 0.
+    return f
+
+
+def realise_slabwise(noise_plane_fn, pk_of_k, N, Lx, Ly, Lz, transfer_fn=None, kinds=(None,), nbins=None,
+                     x_planes=None, workers=4):
+    """
+    box.py:161-193 (+ :374-380 filter, :254-274 / :347 factors, :741-764 moments) plane by plane.
+    ``noise_plane_fn(a) -> (re, im)``: the (N, N) noise planes W[a] (box.py:174-175).
+    ``kinds``: which fields to build from the one spectrum: None = density (Re ifftn), "vel_x" / "vel_y" /
+    "vel_z" (without `fac`), "potential".
+    Returns dict(fields={kind: array}, count, sum1, sum2, edges): each field is the full float64 (N,N,N) cube,
+    or only the x planes listed in ``x_planes`` (shape (len, N, N)); moments (of the density spectrum incl.
+    the filter, Hermitian multiplicities, index = np.digitize) only when ``nbins`` is given.
+    """
+    import scipy.fft
+    from concurrent.futures import ThreadPoolExecutor
+    h = N // 2 + 1
+    kinds = list(kinds)
+    bf = boxfactor(N, Lx, Ly, Lz)
+    bins = pk_bin_edges(N, Lx, Ly, Lz, nbins) if nbins else None
+    m = mode_numbers(N).astype(np.float64)
+    wts = half_weights(N)
+    mabs = np.abs(mode_numbers(N)).astype(np.int64)
+    xs = None if x_planes is None else np.asarray(x_planes, dtype=np.int64)
+    G = {kd: np.empty((h, N, N), dtype=np.complex128) for kd in kinds} if xs is None else None
+
+    def one_block(a_list):
+        part = None if xs is None else {kd: np.zeros((xs.size, N, N)) for kd in kinds}
+        mom = None if bins is None else [np.zeros(bins.size + 1) for _ in range(3)]
+        for a in a_list:
+            re_a, im_a = noise_plane_fn(a)
+            re_m, im_m = (re_a, im_a) if (N - a) % N == a else noise_plane_fn((N - a) % N)
+            k = k_plane(a, N, Lx, Ly, Lz)
+            # P(k) depends on (|m_y|, |m_z|) only and (-m/L)^2 == (m/L)^2 bitwise: evaluate one quadrant
+            kq = k[:N // 2 + 1, :N // 2 + 1]
+            ampq = np.sqrt(np.nan_to_num(np.reshape(pk_of_k(kq.ravel()), kq.shape)) * bf)     # box.py:161-171
+            amp = ampq[mabs[:, None], mabs[None, :]]
+            if transfer_fn is not None:                                                     # box.py:374-379
+                kperp = TWO_PI * np.sqrt((m[a] / Lx) ** 2. + (m[:, None] / Ly) ** 2.)
+                kpar = TWO_PI * m[None, :] / Lz
+                amp = amp * np.nan_to_num(transfer_fn(np.broadcast_to(kperp, (N, N)), np.broadcast_to(kpar, (N, N))))
+            H = hermitian_plane(np.asarray(re_a, np.float64), np.asarray(im_a, np.float64),
+                                np.asarray(re_m, np.float64), np.asarray(im_m, np.float64)) * amp
+            if bins is not None:
+                idx = np.digitize(k.ravel(), bins)
+                power = (H * np.conj(H)).real.ravel() / bf
+                c, s1, s2 = pk_moments(power, idx, bins.size, np.full(power.size, wts[a]))
+                mom[0] += c
+                mom[1] += s1
+                mom[2] += s2
+            for kd in kinds:
+                S = H if kd is None else H * kspace_factor_plane(kd, a, N, Lx, Ly, Lz)
+                g = scipy.fft.ifft2(S)                           # y, z of ifftn (1/N^2)
+                if xs is None:
+                    G[kd][a] = g
+                else:                                            # x of ifftn for the requested planes only
+                    ph = TWO_PI * ((a * xs) % N) / N             # Re(g e^{i ph}) = g.re cos - g.im sin
+                    coef = (wts[a] / N) * np.stack([np.cos(ph), -np.sin(ph)], axis=1)
+                    part[kd] += (coef @ g.view(np.float64).reshape(N * N, 2).T).reshape(xs.size, N, N)
+        return part, mom
+
+    workers = max(1, int(workers))
+    blocks = [list(range(w, h, workers)) for w in range(workers)]
+    with ThreadPoolExecutor(workers) as ex:
+        results = list(ex.map(one_block, blocks))
+    out = {"fields": {}}
+    for kd in kinds:
+        if xs is None:
+            out["fields"][kd] = scipy.fft.irfft(G[kd], n=N, axis=0, workers=-1)
+            G[kd] = None
+        else:
+            out["fields"][kd] = np.sum([r[0][kd] for r in results], axis=0)
+    if bins is not None:
+        out["count"] = np.rint(sum(r[1][0] for r in results)).astype(np.int64)
+        out["sum1"] = sum(r[1][1] for r in results)
+        out["sum2"] = sum(r[1][2] for r in results)
+        out["edges"] = bins
+    return out
+
+
+# --------------------------------------------------------------------------
 # realise_velocity / realise_potential              fastbox/box.py:197-353
 # --------------------------------------------------------------------------
 def velocity_k_port(delta_k, N, Lx, Ly, Lz, fac):
@@ -420,8 +542,8 @@ def halo_mean_count(delta_x, nbar, bias, Lx, Ly, Lz, lognormal_tf=False):
     return np.nan_to_num(mean)
 
 
-def _exp_neg(lam):
-    """exp(-lam) from IEEE + * / only (shared with include/fb_poisson.h: bit-identical)."""
+def _exp_neg_scaled(lam):
+    """exp(-lam) = pm * 2^e from IEEE + * / only (shared with include/fb_poisson.h: bit-identical)."""
     lam = np.asarray(lam, dtype=np.float64)
     n = np.floor(lam * 1.4426950408889634 + 0.5)
     r = (lam - n * 0.693147180369123816490e+00) - n * 1.90821492927058770002e-10
@@ -432,30 +554,62 @@ def _exp_neg(lam):
               1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0,
               1.0 / 6.0, 0.5, 1.0, 1.0):
         p = p * r + c
-    return np.ldexp(p, (-n).astype(np.int64))
+    return p, (-n).astype(np.int64)
 
 
-def poisson_from_uniform(lam, u, kmax=100000):
+def _exp_neg(lam):
+    p, e = _exp_neg_scaled(lam)
+    return np.ldexp(p, e)
+
+
+def poisson_from_uniform(lam, u, kmax=1 << 22):
     """
     PARITY UNPINNED w.r.t. ``np.random.poisson`` (halos.py:116; legacy MT19937
     stream consumes a variable number of uniforms per sample).  Definition
     shared bit-for-bit with the CUDA kernel: inversion by sequential search
         p0 = exp(-lam); count = #{ k : u > sum_{j<=k} p_j },  p_k = p_{k-1} lam / k
-    in float64 using only + * / (no FMA contraction).  lam must be < 700.
+    in float64 using only + * / (no FMA contraction); the term is carried as mantissa * 2^e (rescaled by
+    exact powers of two) so that lam of any size works although exp(-lam) underflows from ~745 on.
     """
     lam = np.asarray(lam, dtype=np.float64)
     u = np.asarray(u, dtype=np.float64)
-    p = _exp_neg(lam)
-    cdf = p.copy()
-    k = np.zeros(lam.shape, dtype=np.int64)
-    active = u > cdf
-    it = 0
-    while np.any(active) and it < kmax:
-        it += 1
-        k = np.where(active, k + 1, k)
-        p = np.where(active, p * lam / k.clip(1), p)
-        cdf = np.where(active, cdf + p, cdf)
-        active = active & (u > cdf) & (p > 0.0)
+    if lam.size and np.any(lam >= 700.0) and np.any(lam < 700.0):         # the header branches at 700
+        out = np.empty(lam.shape, dtype=np.int64)
+        hi = lam >= 700.0
+        out[hi] = poisson_from_uniform(lam[hi], u[hi], kmax)
+        out[~hi] = poisson_from_uniform(lam[~hi], u[~hi], kmax)
+        return out
+    if lam.size and np.all(lam < 700.0):                                   # plain recurrence
+        p = _exp_neg(lam)
+        cdf = p.copy()
+        k = np.zeros(lam.shape, dtype=np.int64)
+        active = u > cdf
+        it = 0
+        while np.any(active) and it < 100000:
+            it += 1
+            k = np.where(active, k + 1, k)
+            p = np.where(active, p * lam / k.clip(1), p)
+            cdf = np.where(active, cdf + p, cdf)
+            active = active & (u > cdf) & (p > 0.0)
+        return k
+    big, small = 1.3407807929942597e+154, 7.458340731200207e-155          # 2^512, 2^-512
+    with np.errstate(all="ignore"):
+        pm, e = _exp_neg_scaled(np.where(lam > 0.0, lam, 1.0))
+        p = np.ldexp(pm, e)
+        cdf = p.copy()
+        k = np.zeros(lam.shape, dtype=np.int64)
+        active = (lam > 0.0) & (u > cdf) & ((p > 0.0) | (k < lam))
+        it = 0
+        while np.any(active) and it < kmax:
+            it += 1
+            k = np.where(active, k + 1, k)
+            pm = np.where(active, pm * lam / k.clip(1), pm)
+            up, down = active & (pm > big), active & (pm < small)
+            pm = np.where(up, pm * small, np.where(down, pm * big, pm))
+            e = e + 512 * up.astype(np.int64) - 512 * down.astype(np.int64)
+            p = np.where(active, np.ldexp(pm, e), p)
+            cdf = np.where(active, cdf + p, cdf)
+            active = active & (u > cdf) & ((p > 0.0) | (k < lam))
     return k
 
 

@@ -74,3 +74,16 @@ def assert_pk_close(got, ref, tol=TOL):
     # error bar: the reference's np.std of a 2-element Hermitian pair is rounding noise, so
     # compare with an absolute floor tied to the bin's power
     assert np.all(np.abs(err[m] - err_r[m]) <= 10 * tol * np.abs(err_r[m]) + 1e-9 * np.abs(pk_r[m]))
+
+
+def deviation_report(got, ref, label=""):
+    """(rel-L2, number of cells off by more than 1e-5 rms, largest deviation / rms); printed for the test log."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    rms = float(np.sqrt(np.mean(ref ** 2)))
+    diff = np.abs(got - ref)
+    nbad = int(np.count_nonzero(diff > 1e-5 * rms))
+    rel = rel_l2(got, ref)
+    print("%s rel-L2 %.3e, cells off by > 1e-5 rms: %d of %d, max |dev|/rms %.3e" % (label, rel, nbad, ref.size,
+                                                                                     diff.max() / rms))
+    return rel, nbad, float(diff.max() / rms)

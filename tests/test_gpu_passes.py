@@ -17,7 +17,7 @@ TOL = 1e-5
 from _util import rel_l2
 
 
-@pytest.mark.parametrize("N", SIZES + [512])
+@pytest.mark.parametrize("N", SIZES + [512, 1024, 2048])
 @pytest.mark.parametrize("sign", [-1, 1])
 def test_rows_and_cols_c2c(gpu, N, sign):
     rng = np.random.default_rng(N + sign)
@@ -35,7 +35,7 @@ def test_rows_and_cols_c2c(gpu, N, sign):
     plan.close()
 
 
-@pytest.mark.parametrize("N", SIZES + [512])
+@pytest.mark.parametrize("N", SIZES + [512, 1024, 2048])
 def test_x_real_passes(gpu, N):
     rng = np.random.default_rng(N)
     ncols = 64 if N <= 64 else 96
@@ -73,4 +73,19 @@ def test_3d_roundtrip_matches_numpy(gpu, N):
     back = np.empty((N, N, N), dtype=np.float32)
     plan.spectrum_to_field(spec, back)
     assert rel_l2(back, f.astype(np.float64)) < TOL
+    plan.close()
+
+
+def test_y_pass_2048_wide_tiles(gpu, monkeypatch):
+    """k_cols_c2c<2048, 8>: the 64-byte-row variant the multi-GPU exchange uses for its NVLink stores."""
+    monkeypatch.setenv("FB_CZ_COLS", "8")
+    N, planes = 2048, 2
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((planes, N, N)) + 1j * rng.standard_normal((planes, N, N))).astype(np.complex64)
+    plan = _lib.Plan(N, 100., 100., 100.)
+    buf = plan.upload(x)
+    plan.fft_pass_c2c(buf, planes, 1, +1)
+    plan.sync()
+    got = plan.download(buf, x.shape, np.complex64)
+    assert rel_l2(got, np.fft.ifft(x.astype(np.complex128), axis=1) * N) < TOL
     plan.close()

@@ -11,7 +11,8 @@ from fastbox_b200 import _lib
 from fastbox_b200 import kspace as ks
 from oracle import restate as R
 
-from _util import (TOL, assert_pk_close, draw_noise, load_golden, pk_function, rel_l2, setup_plan, transfer_fn)
+from _util import (TOL, assert_pk_close, deviation_report, draw_noise, load_golden, pk_function, rel_l2, setup_plan,
+                   transfer_fn)
 
 pytestmark = pytest.mark.gpu
 
@@ -211,7 +212,11 @@ def test_rsd_remap_golden(gpu, name):
     # oracle on the same float32-rounded inputs (the reference result for float64 inputs is the golden)
     ref32 = R.redshift_space_density(d32.astype(np.float64), v32.astype(np.float64), g["z_grid"], float(g["Hz"]))
     assert rel_l2(out, ref32) < TOL
-    assert rel_l2(out, g["rsd0"]) < 50 * TOL          # input rounding moves a few interpolation nodes
+    # ... and against the unmodified reference's float64 output itself: rounding the inputs to float32 moves no
+    # interpolation node in these boxes (the float64 oracle on the rounded inputs is within 3e-8 of the golden)
+    assert rel_l2(ref32, g["rsd0"]) < 1e-7
+    rel, nbad, worst = deviation_report(out, g["rsd0"], "rsd_remap %s vs reference" % name)
+    assert rel < TOL
     np.random.seed(int(g["seed"]) + 100)
     vnl = (120. * np.random.normal(0., 1., (N, N, N))).astype(np.float32)
     plan.rsd_remap(d32, v32, vnl, g["z_grid"], float(g["Hz"]), out)

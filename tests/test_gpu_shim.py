@@ -8,9 +8,10 @@ import pytest
 import fastbox_b200 as fb
 from fastbox_b200.box import CosmoBox, default_cosmo
 
-from _util import TOL, load_golden, rel_l2, transfer_fn
+from _util import TOL, deviation_report, load_golden, rel_l2, transfer_fn
 
 pytestmark = pytest.mark.gpu
+RSD_SHIM_TOL = 100 * TOL      # provisional: tightened to the measured deviation (see the printed report)
 
 
 def test_gaussian_box(gpu):                               # test_box.py:7-38
@@ -62,10 +63,14 @@ def test_box_redshift_space_density(gpu):                 # test_box.py:58-76
     tr = fb.tracers.HITracer(box)
     ln = box.lognormal(box.delta_x * tr.bias_HI())
     ds0 = box.redshift_space_density(delta_x=ln, velocity_z=vel_z, sigma_nl=0.)
-    assert rel_l2(ds0, g["rsd0"]) < 100 * TOL              # float32 inputs move a few interpolation nodes
+    # the inputs here are the DEVICE's float32 log-normal and velocity fields (each within ~2e-7 of the
+    # reference's float64 ones): the deviation of the remapped field is reported cell by cell
+    rel0, nbad0, worst0 = deviation_report(ds0, g["rsd0"], "shim rsd sigma_nl=0")
+    assert rel0 < RSD_SHIM_TOL
     np.random.seed(111)
     ds120 = box.redshift_space_density(delta_x=ln, velocity_z=vel_z, sigma_nl=120.)
-    assert rel_l2(ds120, g["rsd120"]) < 100 * TOL
+    rel1, nbad1, worst1 = deviation_report(ds120, g["rsd120"], "shim rsd sigma_nl=120")
+    assert rel1 < RSD_SHIM_TOL
 
 
 def test_box_transfer_function(gpu):                      # test_box.py:79-96
@@ -137,6 +142,20 @@ def test_halos_and_philox_seed(gpu):
     assert abs((Nh - lam).var() / lam.mean() - 1) < 0.05                 # Poisson variance
     cat = halos.realise_halo_catalogue(Nh, scatter=True)
     assert cat.shape == (Nh.sum(), 3) and cat.min() >= 0 and cat.max() < 2e3
+    # log-normal transform inside halo_count_field (halos.py:105-108): the mean of exp(b delta) is taken on the
+    # device; counts equal the oracle's inversion from the same uniforms, mean field within 1e-5
+    from oracle import restate as R
+    u = np.random.RandomState(5).uniform(0., 1., (64, 64, 64))
+    Nl, mean_l = halos.halo_count_field(box.delta_x, nbar=2e-3, bias=1.3, lognormal=True, uniforms=u, return_mean=True)
+    d32 = box.delta_x.astype(np.float32).astype(np.float64)
+    lam_ref = R.halo_mean_count(d32, 2e-3, np.float64(np.float32(1.3)), box.Lx, box.Ly, box.Lz, lognormal_tf=True)
+    assert rel_l2(mean_l, lam_ref) < TOL
+    ref_counts = R.poisson_from_uniform(lam_ref, u)
+    assert np.mean(Nl != ref_counts) < 1e-4               # the device mean of exp() differs in the last digits
+    assert abs(Nl.mean() / lam_ref.mean() - 1) < 0.01
+    # dense voxels (lambda ~ 1e3: exp(-lambda) underflows; the reference's np.random.poisson has no limit)
+    Nd = halos.halo_count_field(np.zeros((64, 64, 64)), nbar=1e3 / vol, bias=1., uniforms=u)
+    assert abs(Nd.mean() / 1e3 - 1) < 1e-3 and abs(Nd.var() / 1e3 - 1) < 0.02
     # device Philox noise: reproducible, correct spectrum
     d1 = box.realise_density(seed=99)
     d2 = box.realise_density(seed=99)

@@ -124,6 +124,16 @@ def test_c_oracle_matches_numpy_restatement():
     lam1 = np.full(200000, 7.5)
     k = R.poisson_from_uniform(lam1, rng.random(lam1.size))
     assert abs(k.mean() - 7.5) < 0.03 and abs(k.var() - 7.5) < 0.1
+    # large means (exp(-lam) underflows from ~745 on): same answer from C and NumPy, Poisson mean and variance
+    for lam_big in (740.0, 746.0, 1e3, 2e3):
+        lamb = np.full(4000, lam_big)
+        ub = rng.random(lamb.size)
+        outb = np.zeros(lamb.size, np.int32)
+        lib.fb_oracle_poisson(lamb.ctypes.data_as(ctypes.c_void_p), ub.ctypes.data_as(ctypes.c_void_p),
+                              ctypes.c_long(lamb.size), outb.ctypes.data_as(ctypes.c_void_p))
+        assert abs(outb.mean() / lam_big - 1) < 4 * np.sqrt(1.0 / lam_big / lamb.size) + 1e-4
+        assert abs(outb.var() / lam_big - 1) < 0.15
+        assert np.array_equal(outb[:200].astype(np.int64), R.poisson_from_uniform(lamb[:200], ub[:200]))
     # exp(-lam) restatement is accurate to 1 ulp-ish
     lib.fb_oracle_exp_neg.restype = ctypes.c_double
     lib.fb_oracle_exp_neg.argtypes = [ctypes.c_double]
@@ -207,3 +217,34 @@ def test_pca_filter_port_matches_reference_golden():
         assert np.array_equal(np.real(a), g["pca_amps3"])
         assert np.array_equal(np.real(R.pca_filter_port(g["pca_cube"], 3, fit_powerlaw=True)), g["pca_clean3_pl"])
         assert np.array_equal(R.pca_filter_port(g["pca_cube_fg"], 3), g["pca_fg_clean3"])
+
+
+def test_slabwise_restatement_matches_pinned_ports():
+    """realise_slabwise (the 512^3 / 1024^3 checker) == the restatements pinned to the reference above."""
+    N, L = 32, (1e3, 1.5e3, 2e3)
+    re, im = draw_noise(3, N)
+    _, pkf = pk_function(0.8)
+    noise = lambda a: (re[a].astype(np.float32), im[a].astype(np.float32))
+    re32, im32 = re.astype(np.float32).astype(np.float64), im.astype(np.float32).astype(np.float64)
+    kperp, kpar = R.kperp_kpar(N, *L)
+    amp = R.sqrt_pk_half(pkf, N, *L) * np.nan_to_num(transfer_fn(kperp[:N // 2 + 1], kpar))
+    half = R.hermitian_half_from_noise(re32, im32, amp)
+    ref = R.irfft3_axis0(half)
+    kc, pk, err, cnt = R.binned_power_spectrum_lean(half, N, *L, nbins=20)
+    out = R.realise_slabwise(noise, pkf, N, *L, transfer_fn=transfer_fn, nbins=20, workers=3,
+                             kinds=(None, "vel_x", "vel_y", "vel_z", "potential"))
+    assert np.abs(out["fields"][None] - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.array_equal(out["count"][:20], cnt[:20])
+    with np.errstate(all="ignore"):
+        mean = out["sum1"] / out["count"]
+    ok = ~np.isnan(pk)
+    assert np.allclose(mean[1:20][ok], pk[ok], rtol=1e-12)
+    full = R.expand_half_axis0(half)
+    vel = R.velocity_k_port(full, N, *L, 1.0)                   # box.py:251-285
+    for i, kd in enumerate(("vel_x", "vel_y", "vel_z")):
+        want = np.fft.ifftn(vel[i]).real
+        assert np.abs(out["fields"][kd] - want).max() <= 1e-12 * np.abs(want).max()
+    want = np.fft.ifftn(R.potential_k_port(full, N, *L)).real   # box.py:347-352
+    assert np.abs(out["fields"]["potential"] - want).max() <= 1e-12 * np.abs(want).max()
+    part = R.realise_slabwise(noise, pkf, N, *L, transfer_fn=transfer_fn, x_planes=[0, 7, 31], workers=2)
+    assert np.abs(part["fields"][None] - ref[[0, 7, 31]]).max() <= 1e-13 * np.abs(ref).max()

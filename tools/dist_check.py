@@ -27,21 +27,34 @@ def tables(plan, N, L):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"],
+                    help="p2p: exchange inside the library (peer stores over NVLink); nccl: all_to_all_single")
+    ap.add_argument("--sizes", default="64,256")
+    args = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", lr))
     ok = True
-    for N in (64, 256):
+    for N in [int(x) for x in args.sizes.split(",")]:
         L = 2000.0 * N / 1024
         chunks = 2 if (N // 2) // world % 2 == 0 else 1
-        eng = fbd.CudaEngine(N, (L, L, L), rank, world, lr, chunks=chunks)
-        tables(eng.plan, N, L)
-        dr = fbd.DistributedRealiser(eng)
         flags = _lib.F_SQRTPK | _lib.F_FILTER
-        if chunks > 1:
-            field, pk, sums = dr.realise_overlapped(7, flags, want_pk=True)
+        if args.mode == "p2p":
+            dr = fbd.NvlinkRealiser(N, (L, L, L), rank, world, lr, chunks=chunks)
+            tables(dr.plan, N, L)
+            for rep in range(3):                       # repeated steps: both receive buffers, rising epochs
+                fbuf, pk, sums = dr.realise(7, flags, want_pk=True)
+            field = torch.from_numpy(dr.field_host()).cuda()
         else:
-            field, pk, sums = dr.realise(7, flags, want_pk=True)
+            eng = fbd.CudaEngine(N, (L, L, L), rank, world, lr, chunks=chunks)
+            tables(eng.plan, N, L)
+            dr = fbd.DistributedRealiser(eng)
+            if chunks > 1:
+                field, pk, sums = dr.realise_overlapped(7, flags, want_pk=True)
+            else:
+                field, pk, sums = dr.realise(7, flags, want_pk=True)
         torch.cuda.synchronize()
         gathered = [torch.empty_like(field) for _ in range(world)]
         dist.all_gather(gathered, field)
@@ -54,8 +67,8 @@ def main():
             err = np.linalg.norm(full.astype(np.float64) - ref) / np.linalg.norm(ref)
             same_counts = np.array_equal(pk["count"], res["count"])
             pk_err = np.nanmax(np.abs(pk["sum1"] - res["sum1"]) / np.maximum(np.abs(res["sum1"]), 1e-300))
-            print("N=%d world=%d field rel-L2 %.2e, counts equal %s, sum1 rel err %.1e" % (N, world, err, same_counts,
-                                                                                          pk_err), flush=True)
+            print("[%s] N=%d world=%d field rel-L2 %.2e (bit identical %s), counts equal %s, sum1 rel err %.1e" %
+                  (args.mode, N, world, err, np.array_equal(full, ref), same_counts, pk_err), flush=True)
             ok = ok and err < 1e-6 and same_counts and pk_err < 1e-10
             fwd_ref = plan.field_to_spectrum(ref, want_pk=True)
             plan.close()
@@ -70,6 +83,8 @@ def main():
     if rank == 0:
         print("DIST CHECK", "OK" if ok else "FAILED", flush=True)
     dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":
