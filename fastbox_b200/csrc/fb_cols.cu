@@ -69,6 +69,12 @@ static int launch_cols_n(fb_plan* p, const SlabView& vin, const SlabView& vout, 
 int launch_cols_views(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st,
                       int cz_hint) {
     if (nplanes <= 0) return 0;
+    // plain layout on large grids: persistent TMA-pipelined kernel (fb_cols_tma.cu); FB_COLS_TMA=0 keeps the
+    // per-thread LDG/STG kernel below
+    if (vin.ny == 0 && vout.ny == 0 && cz_hint == 0 && env_int("FB_COLS_TMA", FB_COLS_TMA_DEFAULT)) {
+        const int cz = env_int("FB_CZ_TMA", p->N == 512 ? 16 : (p->N == 1024 ? 8 : 4));
+        if (cols_tma_available(p->N, cz)) return launch_cols_tma(p, vin.base[0], vout.base[0], nplanes, sign, cz, st);
+    }
     switch (p->N) {
         case 8: return launch_cols_t<8, 8>(p, vin, vout, nplanes, sign, st);
         case 16: return launch_cols_t<16, 16>(p, vin, vout, nplanes, sign, st);

@@ -18,6 +18,9 @@
 #include "fb_launch.h"
 
 #define FB_DIST_MAX_CHUNKS 16
+#ifndef FB_DIST_XMODE_DEFAULT
+#define FB_DIST_XMODE_DEFAULT 0
+#endif
 #define FB_DIST_HANDLE_BYTES 128
 
 struct fb_dist_state {
@@ -39,6 +42,16 @@ struct fb_dist_state {
     int* err_host;                  // pinned
     int cz_cols;                    // columns per CTA of the exchanging y pass (64-byte rows on NVLink)
     double timeout_s;
+    // exchange mechanism of the inverse transform:
+    //   0 = the y pass stores straight into the peers' receive buffers (one kernel computes and exchanges);
+    //   1 = the y pass writes per-destination blocks locally and the COPY ENGINES push them to the peers
+    //       (cudaMemcpyAsync on one stream per peer): no SM is held by NVLink traffic, so the first pass of the
+    //       next chunk overlaps the transfer of the previous one.
+    int xmode;
+    float2* send;                   // xmode 1: [chunk][dest][plane][y'][z] staging, same size as the work array
+    size_t send_bytes;
+    cudaStream_t cps[FB_MAX_RANKS];
+    cudaEvent_t ev_y[FB_DIST_MAX_CHUNKS], ev_cp[FB_MAX_RANKS];
 };
 
 namespace fb {
@@ -151,6 +164,13 @@ void dist_destroy(fb_plan* p) {
     if (d->ev_ydone) cudaEventDestroy(d->ev_ydone);
     if (d->err_dev) cudaFree(d->err_dev);
     if (d->err_host) cudaFreeHost(d->err_host);
+    if (d->send) cudaFree(d->send);
+    for (int r = 0; r < FB_MAX_RANKS; ++r) {
+        if (d->cps[r]) cudaStreamDestroy(d->cps[r]);
+        if (d->ev_cp[r]) cudaEventDestroy(d->ev_cp[r]);
+    }
+    for (int c = 0; c < FB_DIST_MAX_CHUNKS; ++c)
+        if (d->ev_y[c]) cudaEventDestroy(d->ev_y[c]);
     free(d);
     p->dist = nullptr;
 }
@@ -256,6 +276,12 @@ int fb_dist_init(fb_plan* p, int rank, int world, int with_forward) {
     FB_CUDA(cudaMemset(d->err_dev, 0, sizeof(int)));
     FB_CUDA(cudaMallocHost((void**)&d->err_host, sizeof(int)));
     *d->err_host = 0;
+    d->xmode = env_int("FB_DIST_XMODE", FB_DIST_XMODE_DEFAULT);
+    for (int r = 0; r < world; ++r) {
+        FB_CUDA(cudaStreamCreateWithFlags(&d->cps[r], cudaStreamNonBlocking));
+        FB_CUDA(cudaEventCreateWithFlags(&d->ev_cp[r], cudaEventDisableTiming));
+    }
+    for (int c = 0; c < FB_DIST_MAX_CHUNKS; ++c) FB_CUDA(cudaEventCreateWithFlags(&d->ev_y[c], cudaEventDisableTiming));
     d->cz_cols = env_int("FB_DIST_CZ", N >= 2048 ? 8 : 0);
     d->timeout_s = (double)env_int("FB_DIST_TIMEOUT_S", 20);
     d->peer[rank] = d->block;
@@ -350,6 +376,13 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
     if (phase != 2) {
         if (check_flags(p, flags)) return -1;
         if (ensure_work(p)) return -2;
+        if (d->xmode != 0 && d->send_bytes < p->work_bytes) {
+            if (d->send) FB_CUDA(cudaFree(d->send));
+            d->send = nullptr;
+            d->send_bytes = 0;
+            FB_CUDA(cudaMalloc((void**)&d->send, p->work_bytes));
+            d->send_bytes = p->work_bytes;
+        }
         if (chunks < 1) chunks = 1;
         if (chunks > FB_DIST_MAX_CHUNKS) chunks = FB_DIST_MAX_CHUNKS;
         while (chunks > 1 && d->per % chunks) --chunks;
@@ -383,10 +416,34 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
             }
             FB_CUDA(cudaEventRecord(d->ev_rows[c], d->aux));
             FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_rows[c], 0));
-            for (int r = 0; r < d->world; ++r)
-                vout.base[r] = reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
-            if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), vout, npl, +1, p->stream, d->cz_cols))
-                return -3;
+            if (d->xmode == 0) {
+                for (int r = 0; r < d->world; ++r)
+                    vout.base[r] =
+                        reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
+                if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), vout, npl, +1, p->stream, d->cz_cols))
+                    return -3;
+            } else {
+                // y pass into local per-destination blocks, then one copy-engine transfer per peer
+                float2* send_c = d->send + (size_t)pl0 * N * N;
+                if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), block_view(send_c, ny, npl, N), npl,
+                                      +1, p->stream, 0))
+                    return -3;
+                FB_CUDA(cudaEventRecord(d->ev_y[c], p->stream));
+                const size_t blk = (size_t)npl * ny * N;
+                for (int k = 0; k < d->world; ++k) {
+                    const int r = (d->rank + 1 + k) % d->world;      // start with the neighbour: spreads the links
+                    FB_CUDA(cudaStreamWaitEvent(d->cps[r], d->ev_y[c], 0));
+                    float2* dst = reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
+                    FB_CUDA(cudaMemcpyAsync(dst, send_c + (size_t)r * blk, blk * sizeof(float2), cudaMemcpyDeviceToDevice,
+                                            d->cps[r]));
+                }
+            }
+        }
+        if (d->xmode != 0) {
+            for (int r = 0; r < d->world; ++r) {
+                FB_CUDA(cudaEventRecord(d->ev_cp[r], d->cps[r]));
+                FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[r], 0));
+            }
         }
         if (pk) {
             k_pk_share<<<p->nedges + 1, 32, 0, p->stream>>>(p->h_count, p->h_sums, peer_blocks(d),

@@ -16,6 +16,11 @@ SlabView plain_view(float2* base);
 SlabView block_view(float2* base, int ny, int nplanes, int N);
 int launch_cols_views(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st,
                       int cz_hint);
+bool cols_tma_available(int N, int cz);
+int launch_cols_tma(fb_plan* p, const float2* in, float2* out, int nplanes, int sign, int cz, cudaStream_t st);
+#ifndef FB_COLS_TMA_DEFAULT
+#define FB_COLS_TMA_DEFAULT 0
+#endif
 int launch_x_c2r(fb_plan* p, const XArgs& a);
 int launch_x_r2c(fb_plan* p, const XArgs& a);
 

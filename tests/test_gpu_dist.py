@@ -130,9 +130,14 @@ def _nvlink_tables(plan, N, L, edges, filt=None):
         plan.set_filter(ft.tperp, ft.tpar, ft.tdense)
 
 
-@pytest.mark.parametrize("N,world,chunks", [(32, 1, 1), (64, 1, 4), (32, 2, 1), (64, 2, 2), (64, 4, 2), (128, 8, 2)])
-def test_library_exchange_emulated_ranks(gpu, N, world, chunks):
-    """fb_dist_realise / fb_dist_power_spectrum: `world` plans on one GPU, connected through their handles."""
+@pytest.mark.parametrize("N,world,chunks,xmode", [(32, 1, 1, 0), (64, 1, 4, 0), (32, 2, 1, 0), (64, 2, 2, 0),
+                                                  (64, 4, 2, 0), (128, 8, 2, 0), (64, 2, 2, 1), (128, 8, 4, 1)])
+def test_library_exchange_emulated_ranks(gpu, monkeypatch, N, world, chunks, xmode):
+    """
+    fb_dist_realise / fb_dist_power_spectrum: `world` plans on one GPU, connected through their handles.
+    xmode 0: the y pass stores into the peers' buffers; 1: local blocks + copy-engine transfers.
+    """
+    monkeypatch.setenv("FB_DIST_XMODE", str(xmode))
     L = (1e3, 1e3, 1e3)
     flags = _lib.F_SQRTPK | _lib.F_FILTER
     plan, edges = setup_plan(N, L, 0.8, nbins=20, filt=transfer_fn, exact_below=4096)

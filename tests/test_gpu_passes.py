@@ -89,3 +89,25 @@ def test_y_pass_2048_wide_tiles(gpu, monkeypatch):
     got = plan.download(buf, x.shape, np.complex64)
     assert rel_l2(got, np.fft.ifft(x.astype(np.complex128), axis=1) * N) < TOL
     plan.close()
+
+
+@pytest.mark.parametrize("N,cz", [(512, 8), (512, 16), (1024, 4), (1024, 8), (2048, 4)])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_y_pass_tma_pipelined(gpu, monkeypatch, N, cz, sign):
+    """Persistent TMA-pipelined y pass (fb_cols_tma.cu) == numpy.fft and == the per-thread kernel bit for bit."""
+    planes = 5                                      # 5 * N/cz tiles: several tiles per CTA, both buffers reused
+    rng = np.random.default_rng(N + cz)
+    x = (rng.standard_normal((planes, N, N)) + 1j * rng.standard_normal((planes, N, N))).astype(np.complex64)
+    plan = _lib.Plan(N, 100., 100., 100.)
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("FB_COLS_TMA", tma)
+        monkeypatch.setenv("FB_CZ_TMA", str(cz))
+        buf = plan.upload(x)
+        plan.fft_pass_c2c(buf, planes, 1, sign)
+        plan.sync()
+        out[tma] = plan.download(buf, x.shape, np.complex64)
+    ref = np.fft.fft(x.astype(np.complex128), axis=1) if sign < 0 else np.fft.ifft(x.astype(np.complex128), axis=1) * N
+    assert rel_l2(out["1"], ref) < TOL
+    assert np.array_equal(out["1"], out["0"])
+    plan.close()
