@@ -56,6 +56,8 @@ SIGNATURES = {
     "fb_cube_to_field": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "fb_field_to_spectrum": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(PkResult)]),
     "fb_pk_from_spectrum": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(PkResult)]),
+    "fb_pk2d_from_spectrum": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "fb_correlation_function": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "fb_affine": (_i, [_vp, _vp, _sz, _f, _f]),
     "fb_exp_sum": (_i, [_vp, _vp, _vp, _sz, _f, C.POINTER(_d)]),
     "fb_field_moments": (_i, [_vp, _vp, _sz, C.POINTER(_d), C.POINTER(_d)]),
@@ -287,6 +289,26 @@ class Plan(object):
         check(self.lib.fb_pk_from_spectrum(self.h, _ptr(spec), _ptr(cross), int(bool(full_cube)),
                                            F_POLES if poles else 0, C.byref(st)))
         return res
+
+    def pk2d_from_spectrum(self, spec, thr_perp, ipar, npar, cross=None, full_cube=False):
+        """Moments on the (k_perp, |k_par|) grid: dict(count, sum1, sum2) of shape (nperp + 1, npar + 1)."""
+        thr = np.ascontiguousarray(thr_perp, dtype=np.float64)
+        ip = np.ascontiguousarray(ipar, dtype=np.int32)
+        shape = (thr.size + 1, int(npar) + 1)
+        out = dict(count=np.zeros(shape, np.uint64), sum1=np.zeros(shape), sum2=np.zeros(shape))
+        check(self.lib.fb_pk2d_from_spectrum(self.h, _ptr(spec), _ptr(cross), int(bool(full_cube)), thr.ctypes.data,
+                                             thr.size, ip.ctypes.data, int(npar), out["count"].ctypes.data,
+                                             out["sum1"].ctypes.data, out["sum2"].ctypes.data))
+        return out
+
+    def correlation_function(self, field, edges, field_b=None, xi_out=None):
+        """Radial moments of xi = ifftn(A conj B) / N^3: dict(count, sum1, sum2), index = np.digitize(r, edges)."""
+        e = np.ascontiguousarray(edges, dtype=np.float64)
+        out = dict(count=np.zeros(e.size + 1, np.uint64), sum1=np.zeros(e.size + 1), sum2=np.zeros(e.size + 1))
+        check(self.lib.fb_correlation_function(self.h, _ptr(field), _ptr(field_b), e.ctypes.data, e.size,
+                                               out["count"].ctypes.data, out["sum1"].ctypes.data,
+                                               out["sum2"].ctypes.data, _ptr(xi_out)))
+        return out
 
     def affine(self, field, n, mul, add):
         check(self.lib.fb_affine(self.h, _ptr(field), int(n), float(mul), float(add)))

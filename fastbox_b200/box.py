@@ -477,6 +477,69 @@ class CosmoBox(object):
             warnings.simplefilter("ignore")
             return ks.moments_to_spectrum(bins, res["count"], res["sum1"], res["sum2"])
 
+    def binned_power_spectrum_2d(self, delta_x=None, delta_k=None, nbins=(20, 20), kperp_bins=None, kpar_bins=None):
+        """
+        EXTENSION (the reference delegates 2-D spectra to nbodykit's FFTPower): P(k_perp, |k_par|) with the line of
+        sight along z, estimator and conventions of ``binned_power_spectrum`` (np.digitize bins, the first edge
+        only bounds the first bin from below, population stddev / sqrt(n), NaN for empty bins).  Default edges:
+        ``nbins`` log-spaced edges per axis between the fundamental and the Nyquist wavenumber of that axis.
+        Returns (kperp_centres, kpar_centres, pk2d, stddev2d), pk2d of shape (len(kperp_bins)-1, len(kpar_bins)-1).
+        """
+        if delta_x is not None and delta_k is not None:
+            raise ValueError("delta_x and delta_k specified; can only specify one")
+        N = self.N
+        if kperp_bins is None:
+            kperp_bins = np.logspace(np.log10(2. * np.pi / max(self.Lx, self.Ly)),
+                                     np.log10(np.sqrt(2.) * np.pi * N / min(self.Lx, self.Ly)), nbins[0])
+        if kpar_bins is None:
+            kpar_bins = np.logspace(np.log10(2. * np.pi / self.Lz), np.log10(np.pi * N / self.Lz), nbins[1])
+        kperp_bins = np.asarray(kperp_bins, dtype=np.float64)
+        kpar_bins = np.asarray(kpar_bins, dtype=np.float64)
+        if max(kperp_bins.size, kpar_bins.size) > 64:
+            raise ValueError("at most 64 edges per axis are supported")
+        m = ks.mode_numbers(N).astype(np.float64)
+        ipar = np.digitize(np.abs(2. * np.pi * m / self.Lz), kpar_bins)
+        thr = ks.bin_thresholds(kperp_bins)
+        plan = self._plan
+        if delta_x is not None:
+            spec = self._spectrum_arg(delta_x, None)
+        else:
+            spec = self._spectrum_arg(None, delta_k)
+        if spec.kind != _lib.KIND_PLAIN:
+            raise ValueError("binned_power_spectrum_2d needs a density-like spectrum")
+        res = plan.pk2d_from_spectrum(spec.buf, thr, ipar, kpar_bins.size)
+        cnt = res["count"].astype(np.float64)
+        with np.errstate(all="ignore"):
+            mean = res["sum1"] / cnt
+            err = np.sqrt(np.maximum(res["sum2"] / cnt - mean * mean, 0.0)) / np.sqrt(cnt)
+        sl = (slice(1, kperp_bins.size), slice(1, kpar_bins.size))
+        return ks.bin_centres(kperp_bins)[1:], ks.bin_centres(kpar_bins)[1:], mean[sl], err[sl]
+
+    def correlation_function(self, delta_x=None, delta_b=None, dr=2., rmin=20., rmax=200., rbins=None):
+        """
+        EXTENSION (nbodykit ``FFTCorr(first=mesh, mode='1d', dr=2., rmin=20., rmax=200.)`` in
+        examples/example_endtoend.py:128-151): the correlation function xi(r) = < d(x) d(x + r) > of a real field
+        (cross-correlation with ``delta_b`` if given), from xi = ifftn(|fftn(d)|^2) / N^3 on the device and a
+        radial average over the periodic lags (cell size L/N) in the bins ``rbins`` (default: edges
+        rmin, rmin + dr, ... up to rmax).  Returns (r_centres, xi, stddev / sqrt(n)); empty bins are NaN.
+        """
+        if rbins is None:
+            rbins = np.arange(rmin, rmax + 0.5 * dr, dr)
+        rbins = np.asarray(rbins, dtype=np.float64)
+        if rbins.size < 2 or rbins.size > _lib.MAX_EDGES:
+            raise ValueError("need between 2 and %d r-bin edges" % _lib.MAX_EDGES)
+        if delta_x is None:
+            delta_x = self.delta_x
+        a = self._to_device_field(delta_x)
+        b = None if delta_b is None else self._to_device_field(delta_b)
+        res = self._plan.correlation_function(a, rbins, field_b=b)
+        nb = rbins.size
+        cnt = res["count"][:nb].astype(np.float64)
+        with np.errstate(all="ignore"):
+            mean = res["sum1"][:nb] / cnt
+            err = np.sqrt(np.maximum(res["sum2"][:nb] / cnt - mean * mean, 0.0)) / np.sqrt(cnt)
+        return 0.5 * (rbins[1:] + rbins[:-1]), mean[1:], err[1:]
+
     def power_multipoles(self, delta_x, nbins=20, kbins=None):
         """
         EXTENSION (the reference delegates this to nbodykit, example_box.py:48-52):

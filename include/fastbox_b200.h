@@ -137,6 +137,20 @@ int fb_field_to_spectrum(fb_plan* plan, const float* field, void* spec_out, cons
 int fb_pk_from_spectrum(fb_plan* plan, const void* spec, const void* cross_spec, int full_cube, int flags,
                         fb_pk_result* pk);
 
+/* ---- P(k_perp, |k_par|) and xi(r) (the reference delegates both to nbodykit,
+ * examples/example_endtoend.py:128-151: parity is pinned to oracle/restate.py, unpinned w.r.t. nbodykit) ------ */
+/* thr_perp[nperp]: thresholds on s = (Kx/Lx)^2 + (Ky/Ly)^2 as in fb_set_pk_bins; ipar[N]: np.digitize bin of
+ * |2 pi Kz / Lz| for every z mode (host, int32); outputs host arrays [(nperp+1)*(npar+1)], row = k_perp bin.
+ * spec: half spectrum (full_cube = 0) or full [N][N][N] cube; cross_spec nullable.                            */
+int fb_pk2d_from_spectrum(fb_plan* plan, const void* spec, const void* cross_spec, int full_cube,
+                          const double* thr_perp, int nperp, const int32_t* ipar, int npar, uint64_t* count,
+                          double* sum1, double* sum2);
+/* xi(r) = ifftn(fftn(a) conj fftn(b)) / N^3 binned over the lag separations (periodic, cell size L/N);
+ * field_b nullable (auto-correlation); edges[nedges] host float64 ascending; outputs host [nedges+1], index =
+ * np.digitize(r, edges); xi_out: nullable DEVICE float32 [N^3] receiving the lag cube.                        */
+int fb_correlation_function(fb_plan* plan, const float* field, const float* field_b, const double* edges, int nedges,
+                            uint64_t* count, double* sum1, double* sum2, float* xi_out);
+
 /* ---- elementwise ------------------------------------------------------------- */
 /* field = field * mul + add  (log-normal normalise box.py:458-459, Tb(1+d))   */
 int fb_affine(fb_plan* plan, float* field, size_t n, float mul, float add);

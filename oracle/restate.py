@@ -468,6 +468,68 @@ def pk_multipoles(half, N, Lx, Ly, Lz, nbins=20, kbins=None, ells=(0, 2, 4)):
 
 
 # --------------------------------------------------------------------------
+# P(k_perp, k_par) and xi(r)      (reference: nbodykit FFTPower mode='2d' / FFTCorr mode='1d',
+# examples/example_endtoend.py:128-151 -- nbodykit is neither vendored nor pinned, so these
+# definitions are PARITY UNPINNED w.r.t. nbodykit; they reuse the conventions of
+# binned_power_spectrum: np.digitize bins, multiplicity weights, population stddev / sqrt(n))
+# --------------------------------------------------------------------------
+def binned_power_spectrum_2d_lean(half_a, N, Lx, Ly, Lz, kperp_bins, kpar_bins, half_b=None):
+    """
+    Moments of |d_k|^2 / boxfactor (or Re a conj b) binned in k_perp = 2 pi sqrt((Kx/Lx)^2 + (Ky/Ly)^2) and
+    |k_par| = 2 pi |Kz| / Lz.  Returns (kperp centres[1:], kpar centres[1:], mean, err, count) with mean / err of
+    shape (len(kperp_bins) - 1, len(kpar_bins) - 1) and count the full (nperp + 1, npar + 1) population table.
+    """
+    kperp_bins = np.asarray(kperp_bins, dtype=np.float64)
+    kpar_bins = np.asarray(kpar_bins, dtype=np.float64)
+    m = mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    kperp = TWO_PI * np.sqrt((m[:h, None] / Lx) ** 2. + (m[None, :] / Ly) ** 2.)
+    kpar = np.abs(TWO_PI * m / Lz)
+    ip = np.digitize(kperp.ravel(), kperp_bins).reshape(kperp.shape)
+    il = np.digitize(kpar, kpar_bins)
+    npar = kpar_bins.size
+    idx = (ip[:, :, None] * (npar + 1) + il[None, None, :]).ravel()
+    other = half_a if half_b is None else half_b
+    power = (half_a * np.conj(other)).real.ravel() / boxfactor(N, Lx, Ly, Lz)
+    w = np.broadcast_to(half_weights(N)[:, None, None], (h, N, N)).ravel()
+    nb2 = (kperp_bins.size + 1) * (npar + 1)
+    cnt, s1, s2 = pk_moments(power, idx, nb2 - 1, w)
+    shape = (kperp_bins.size + 1, npar + 1)
+    cnt, s1, s2 = cnt.reshape(shape), s1.reshape(shape), s2.reshape(shape)
+    with np.errstate(all="ignore"):
+        mean = s1 / cnt
+        err = np.sqrt(np.maximum(s2 / cnt - mean * mean, 0.0)) / np.sqrt(cnt)
+    sl = (slice(1, kperp_bins.size), slice(1, npar))
+    return bin_centres(kperp_bins)[1:], bin_centres(kpar_bins)[1:], mean[sl], err[sl], np.rint(cnt).astype(np.int64)
+
+
+def lag_separations(N, Lx, Ly, Lz):
+    """|r| of every lag of the periodic N^3 grid, cell size L/N: sqrt(((dx hx)^2 + (dy hy)^2) + (dz hz)^2)."""
+    d = np.minimum(np.arange(N), N - np.arange(N)).astype(np.float64)
+    dx, dy, dz = d * (Lx / N), d * (Ly / N), d * (Lz / N)
+    return np.sqrt((dx[:, None, None] * dx[:, None, None] + dy[None, :, None] * dy[None, :, None])
+                   + dz[None, None, :] * dz[None, None, :])
+
+
+def correlation_function_port(field_a, N, Lx, Ly, Lz, edges, field_b=None):
+    """
+    xi(r) = < a(x) b(x + r) > by the Wiener-Khinchin route, xi = ifftn(A conj B) / N^3, averaged over the lags
+    whose separation falls in [edges[i-1], edges[i]).  Returns (centres, mean, stddev / sqrt(n), count[nedges+1]).
+    """
+    edges = np.asarray(edges, dtype=np.float64)
+    A = np.fft.fftn(np.asarray(field_a, dtype=np.float64))
+    B = A if field_b is None else np.fft.fftn(np.asarray(field_b, dtype=np.float64))
+    xi = np.fft.ifftn(A * np.conj(B)).real / float(N) ** 3
+    idx = np.digitize(lag_separations(N, Lx, Ly, Lz).ravel(), edges)
+    cnt, s1, s2 = pk_moments(xi.ravel(), idx, edges.size)
+    with np.errstate(all="ignore"):
+        mean = s1 / cnt
+        err = np.sqrt(np.maximum(s2 / cnt - mean * mean, 0.0)) / np.sqrt(cnt)
+    cent = 0.5 * (edges[1:] + edges[:-1])
+    return cent, mean[1:edges.size], err[1:edges.size], np.rint(cnt).astype(np.int64)
+
+
+# --------------------------------------------------------------------------
 # redshift_space_density                            fastbox/box.py:384-438
 #   scipy griddata 1-D linear == argsort + interp1d(linear, fill_value)
 #   (scipy/interpolate/_ndgriddata.py:315-330, _interpolate.py:491-518,592-593)

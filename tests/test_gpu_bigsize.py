@@ -145,10 +145,12 @@ def test_2048_kspace_kernels_on_slabs_vs_oracle(gpu):
     plan, edges = setup_plan(N, L, 0.8, nbins=nb, filt=transfer_fn)
     bf = R.boxfactor(N, *L)
     m = R.mode_numbers(N).astype(np.float64)
-    for a0, na in ((0, 2), (N // 2, 1)):
+    # the Gaussian k_perp filter puts the Nyquist plane ~50 orders of magnitude below float32's range (it
+    # comes out as exact zeros): that plane is checked without the filter
+    for a0, na, filt in ((0, 2, True), (N // 2, 1, False)):
         plan.set_slab(a0, na, 0, N)
         work = plan.alloc(na * N * N * 8)
-        res = plan.realise_local_kspace(seed, F.F_SQRTPK | F.F_FILTER, work, None, 0, want_pk=True)
+        res = plan.realise_local_kspace(seed, F.F_SQRTPK | (F.F_FILTER if filt else 0), work, None, 0, want_pk=True)
         got = plan.download(work, (na, N, N), np.complex64)
         cnt = np.zeros(nb + 1)
         s1 = np.zeros(nb + 1)
@@ -160,7 +162,8 @@ def test_2048_kspace_kernels_on_slabs_vs_oracle(gpu):
             k = R.k_plane(a, N, *L)
             amp = np.sqrt(np.nan_to_num(pkf(k.ravel()).reshape(k.shape)) * bf)
             kperp = 2 * np.pi * np.sqrt((m[a] / L[0]) ** 2. + (m[:, None] / L[1]) ** 2.)
-            amp = amp * np.nan_to_num(transfer_fn(np.broadcast_to(kperp, (N, N)), 2 * np.pi * m[None, :] / L[2]))
+            if filt:
+                amp = amp * np.nan_to_num(transfer_fn(np.broadcast_to(kperp, (N, N)), 2 * np.pi * m[None, :] / L[2]))
             H = (re + 1j * im) * amp
             want = np.fft.ifft2(H) * (N * N)                 # z rows and y columns, unnormalised
             assert rel_l2(got[i], want) < TOL, a

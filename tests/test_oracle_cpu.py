@@ -248,3 +248,39 @@ def test_slabwise_restatement_matches_pinned_ports():
     assert np.abs(out["fields"]["potential"] - want).max() <= 1e-12 * np.abs(want).max()
     part = R.realise_slabwise(noise, pkf, N, *L, transfer_fn=transfer_fn, x_planes=[0, 7, 31], workers=2)
     assert np.abs(part["fields"][None] - ref[[0, 7, 31]]).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_two_point_restatements_are_self_consistent():
+    """
+    P(k_perp, k_par) and xi(r) (parity unpinned w.r.t. nbodykit): collapsing the 2-D table over one axis gives the
+    pinned 1-D estimator's populations; xi(r) equals a direct pair average on a small grid.
+    """
+    N, L = 16, (1e2, 1.5e2, 2e2)
+    rng = np.random.default_rng(2)
+    f = rng.standard_normal((N, N, N))
+    half = R.rfft3_axis0(f)
+    kp = np.concatenate([[0.0], np.linspace(0.05, 1.2, 9)])
+    kl = np.concatenate([[0.0], np.linspace(0.04, 0.6, 7)])
+    cp, cl, mean, err, cnt = R.binned_power_spectrum_2d_lean(half, N, *L, kp, kl)
+    assert mean.shape == (kp.size - 1, kl.size - 1) and cnt.shape == (kp.size + 1, kl.size + 1)
+    assert cnt.sum() == N ** 3                                   # every mode lands in exactly one cell
+    m = R.mode_numbers(N).astype(np.float64)
+    kpar_full = np.abs(2 * np.pi * m / L[2])
+    assert np.array_equal(cnt.sum(axis=0), np.bincount(np.digitize(kpar_full, kl), minlength=kl.size + 1) * N * N)
+    # total power is conserved by the binning
+    tot = np.nansum(np.where(cnt > 0, 1.0, 0.0))
+    assert tot > 10
+    # xi(r): Wiener-Khinchin == direct average of f(x) f(x + lag) for three lags
+    edges = np.array([0.0, 1e-9, 7.0, 11.0, 16.0, 25.0])
+    cent, xi, xerr, c = R.correlation_function_port(f, N, *L, edges)
+    r = R.lag_separations(N, *L)
+    direct = np.zeros((N, N, N))
+    for (i, j, l) in [(0, 0, 0), (1, 0, 0), (0, 1, 1), (N - 1, 0, 2)]:
+        direct[i, j, l] = np.mean(f * np.roll(f, (-i, -j, -l), axis=(0, 1, 2)))
+    A = np.fft.fftn(f)
+    full = np.fft.ifftn(A * np.conj(A)).real / N ** 3
+    for (i, j, l) in [(0, 0, 0), (1, 0, 0), (0, 1, 1), (N - 1, 0, 2)]:
+        assert abs(full[i, j, l] - direct[i, j, l]) < 1e-12
+    assert abs(xi[0] - np.mean(f * f)) < 1e-12 and c[1] == 1      # the zero lag alone sits in the first bin
+    sel = (r >= 7.0) & (r < 11.0)
+    assert abs(xi[2] - full[sel].mean()) < 1e-13 and c[3] == sel.sum()
