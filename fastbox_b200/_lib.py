@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfastbox_b200.so")
+LIB_PATH = os.environ.get("FB_LIB") or os.path.join(_HERE, "libfastbox_b200.so")     # FB_LIB: A/B builds
 
 # flags / kinds (mirror include/fastbox_b200.h)
 KIND_PLAIN, KIND_VEL_X, KIND_VEL_Y, KIND_VEL_Z, KIND_POTENTIAL = 0, 1, 2, 3, 4

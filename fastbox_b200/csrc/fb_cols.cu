@@ -130,6 +130,8 @@ static int launch_x_n(fb_plan* p, const XArgs& a, bool inv, int dflt) {
 }
 
 static int launch_x(fb_plan* p, const XArgs& a, bool inv) {
+    // plain layouts on large grids: persistent TMA-pipelined kernels (fb_x_tma.cu); FB_X_TMA=0 keeps the per-thread ones
+    if (env_int("FB_X_TMA", FB_X_TMA_DEFAULT) && x_tma_available(p, a, inv)) return launch_x_tma(p, a, inv);
     switch (p->N) {
         case 8: return launch_x_t<8, 32>(p, a, inv);
         case 16: return launch_x_t<16, 32>(p, a, inv);

@@ -32,10 +32,53 @@ namespace fb {
 #define FB_SYNC() ((void)0)
 #endif
 
-FB_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-FB_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on the packed 2 x fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2): one issue slot per
+// complex add, two per complex multiply (the rotated operand (-y, x) and a scalar broadcast are operand modifiers
+// in SASS, not instructions).  The FFT kernels are issue-slot bound next to HBM, and ~3/4 of their instructions
+// were scalar FADD / FMUL / FFMA.  FB_PACKED_F32=0 (and the host build) keeps the scalar forms.
+#ifndef FB_PACKED_F32
+#define FB_PACKED_F32 1
+#endif
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && FB_PACKED_F32
+#define FB_PK2 1
+#else
+#define FB_PK2 0
+#endif
+FB_DEV float2 cadd(float2 a, float2 b) {
+#if FB_PK2
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+FB_DEV float2 csub(float2 a, float2 b) {
+#if FB_PK2
+    return __ffma2_rn(b, make_float2(-1.f, -1.f), a);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 FB_DEV float2 cmul(float2 a, float2 b) {
+#if FB_PK2
+    return __ffma2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x), __fmul2_rn(make_float2(a.x, a.x), b));
+#else
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+#endif
+}
+// a * (c + i s) with compile-time-known c, s
+FB_DEV float2 cmul_const(float2 a, float c, float s) {
+#if FB_PK2
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(s, s), __fmul2_rn(a, make_float2(c, c)));
+#else
+    return make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.x, s, a.y * c));
+#endif
+}
+FB_DEV float2 cscale(float2 a, float h) {
+#if FB_PK2
+    return __fmul2_rn(a, make_float2(h, h));
+#else
+    return make_float2(a.x * h, a.y * h);
+#endif
 }
 FB_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
@@ -59,16 +102,16 @@ FB_DEV float2 ctwiddle(float2 a) {
         return a;
     } else if constexpr (M16 == 8) {          // * (S i)
         return S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
-    } else if constexpr (M16 == 4) {          // * (1 + S i)/sqrt2
+    } else if constexpr (M16 == 4) {          // * (1 + S i)/sqrt2 = (a + S i a) / sqrt2
         constexpr float h = 0.70710678118654752440f;
-        return S > 0 ? make_float2(h * (a.x - a.y), h * (a.x + a.y)) : make_float2(h * (a.x + a.y), h * (a.y - a.x));
-    } else if constexpr (M16 == 12) {         // * (-1 + S i)/sqrt2
+        return cscale(cadd(a, S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x)), h);
+    } else if constexpr (M16 == 12) {         // * (-1 + S i)/sqrt2 = -(a - S i a) / sqrt2
         constexpr float h = 0.70710678118654752440f;
-        return S > 0 ? make_float2(-h * (a.x + a.y), h * (a.x - a.y)) : make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+        return cscale(cadd(a, S > 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x)), -h);
     } else {
         constexpr float c = cos_pi16(M16);
         constexpr float s = (S > 0 ? 1.f : -1.f) * sin_pi16(M16);
-        return make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.x, s, a.y * c));
+        return cmul_const(a, c, s);
     }
 }
 

@@ -19,7 +19,12 @@ int launch_cols_views(fb_plan* p, const SlabView& vin, const SlabView& vout, int
 bool cols_tma_available(int N, int cz);
 int launch_cols_tma(fb_plan* p, const float2* in, float2* out, int nplanes, int sign, int cz, cudaStream_t st);
 #ifndef FB_COLS_TMA_DEFAULT
-#define FB_COLS_TMA_DEFAULT 0
+#define FB_COLS_TMA_DEFAULT 1
+#endif
+bool x_tma_available(const fb_plan* p, const XArgs& a, bool inverse);
+int launch_x_tma(fb_plan* p, const XArgs& a, bool inverse);
+#ifndef FB_X_TMA_DEFAULT
+#define FB_X_TMA_DEFAULT 0
 #endif
 int launch_x_c2r(fb_plan* p, const XArgs& a);
 int launch_x_r2c(fb_plan* p, const XArgs& a);

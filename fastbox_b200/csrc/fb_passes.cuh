@@ -20,6 +20,12 @@ enum { SRC_NOISE = 0, SRC_PHILOX = 1, SRC_SPEC = 2, SRC_CUBE = 3 };
 #ifndef FB_ROWS_INV_MINB
 #define FB_ROWS_INV_MINB FB_ROWS_MINB
 #endif
+#ifndef FB_ROWS_NOISE_QB
+#define FB_ROWS_NOISE_QB 8
+#endif
+#ifndef FB_ROWS_NOISE_STOCKHAM
+#define FB_ROWS_NOISE_STOCKHAM 0     // noise-cube prologue loads in Stockham order (0: quad order + shared-memory park)
+#endif
 
 template <int N>
 struct RowGeom {
@@ -492,8 +498,58 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
     if (fast && (A.flags & FB_F_FILTER)) fast_base *= __ldg(&A.K.tperp[a * N + b]);
 
     bool fast_done = false;
-    if constexpr (T > 1 && (SRC == SRC_NOISE || SRC == SRC_PHILOX)) {
+#if FB_ROWS_NOISE_STOCKHAM
+    if constexpr (T > 1 && SRC == SRC_NOISE) {
         if (fast) {
+            // Noise cubes, common configuration: every thread loads ITS Stockham-order modes c = t + T*q straight
+            // from HBM (a warp still touches 128 consecutive bytes per request, so the wavefront count of the
+            // loads equals that of 16-byte quad loads) and parks the combined spectrum at its natural position:
+            // consecutive lanes write consecutive modes.  The quad-order version parked with 32-byte lane
+            // strides (4x the wavefronts of a dense store); the L1 data pipe is what limits this kernel.
+            fast_done = true;
+            const bool has_f = (A.flags & FB_F_FILTER) != 0, has_s = (A.flags & FB_F_SQRTPK) != 0;
+            const int mt = (N - t) & (N - 1);                             // mirror cell of mode t
+            const float* re_g = A.re + row_g + t;
+            const float* im_g = A.im + row_g + t;
+            const float* re_m = A.re + row_m + mt + (t == 0 ? N : 0);     // mirror of t + T*q: mt - T*q (q >= 1)
+            const float* im_m = A.im + row_m + mt + (t == 0 ? N : 0);
+            constexpr int QB = FB_ROWS_NOISE_QB;                          // modes per batch of loads (register budget)
+            const bool do_store = A.spec_out != nullptr && rvalid;
+            float2* park = sm + sl(t);
+#pragma unroll
+            for (int q0 = 0; q0 < P; q0 += QB) {
+                float gr[QB], gi[QB], mr[QB], mi[QB];
+#pragma unroll
+                for (int i = 0; i < QB; ++i) {
+                    const int q = q0 + i;
+                    gr[i] = __ldg(re_g + T * q);
+                    gi[i] = __ldg(im_g + T * q);
+                    mr[i] = q == 0 ? __ldg(A.re + row_m + mt) : __ldg(re_m - T * q);
+                    mi[i] = q == 0 ? __ldg(A.im + row_m + mt) : __ldg(im_m - T * q);
+                }
+#pragma unroll
+                for (int i = 0; i < QB; ++i) {
+                    const int q = q0 + i;
+                    const int c = t + T * q;
+                    float f = fast_base;
+                    if (has_f) f *= __ldg(A.K.tpar + c);
+                    if (has_s) {
+                        const int mc = q < P / 2 ? c : c - N;             // |m_c| (c = N/2 either way)
+                        float am = sqrtp_bittable_nz(A.K, sab_f + (float)(mc * mc) * A.K.inv_lz2);
+                        if (q == 0 && dc_row && t == 0) am = 0.f;         // nan_to_num(P(0)) = 0, box.py:167
+                        f *= am;
+                    }
+                    const float2 h = make_float2((gr[i] + mr[i]) * f, (gi[i] - mi[i]) * f);
+                    if (do_store) A.spec_out[row_local + c] = h;
+                    if constexpr (T % 16 == 0) park[q * RowLayout<N>::pstride(T)] = h;     // natural order, dense per warp
+                    else sm[sl(c)] = h;
+                }
+            }
+        }
+    }
+#endif
+    if constexpr (T > 1 && (SRC == SRC_NOISE || SRC == SRC_PHILOX)) {
+        if (fast && !fast_done) {
             // Common configuration (bit-table sqrt(P) or none, separable filter or none, plain
             // field).  The loop body is free of branches (options are predicated loads / selects),
             // so the loads of later quads are scheduled above the arithmetic of earlier ones.

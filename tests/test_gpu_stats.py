@@ -58,7 +58,9 @@ def test_pk2d_matches_oracle(gpu, N, L):
             assert np.all(np.abs(got[ok] - mean[ok]) <= TOL * np.abs(mean[ok]))
         else:                                   # a cross spectrum changes sign: compare against the bin's scatter
             assert np.all(np.abs(got[ok] - mean[ok]) <= TOL * (np.abs(mean[ok]) + err[ok] * np.sqrt(cnt[1:kp.size, 1:kl.size][ok])))
-        assert np.all(np.abs(gerr[ok] - err[ok]) <= 10 * TOL * err[ok] + 1e-9 * scale)
+        # error bars: a bin holding one Hermitian pair has stddev == 0 exactly on the device and float64 rounding
+        # noise (~1e-8 of the bin's power) in NumPy's two-pass formula: floor tied to the bin's own power
+        assert np.all(np.abs(gerr[ok] - err[ok]) <= 10 * TOL * err[ok] + 1e-6 * np.abs(mean[ok]) + 1e-9 * scale)
     # full-cube input gives the same table (every mode counted once instead of twice)
     full = np.fft.fftn(f).astype(np.complex64)
     res_full = plan.pk2d_from_spectrum(plan.upload(full), thr, ipar, kl.size, full_cube=True)
