@@ -62,6 +62,7 @@ SIGNATURES = {
     "fb_exp_sum": (_i, [_vp, _vp, _vp, _sz, _f, C.POINTER(_d)]),
     "fb_field_moments": (_i, [_vp, _vp, _sz, C.POINTER(_d), C.POINTER(_d)]),
     "fb_rsd_remap": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp]),
+    "fb_beam_set": (_i, [_vp, _vp]),
     "fb_beam_convolve": (_i, [_vp, _vp, _vp, _vp]),
     "fb_halo_counts": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "fb_counts_to_field": (_i, [_vp, _vp, _sz, _f, _f, _vp]),
@@ -328,7 +329,12 @@ class Plan(object):
         check(self.lib.fb_rsd_remap(self.h, _ptr(delta), _ptr(vel_z), _ptr(vel_nl), z.ctypes.data, float(Hz),
                                     _ptr(out)))
 
+    def beam_set(self, beam):
+        """Transform and keep the beam cube (float32 [N][N][N]); later beam_convolve(None, ...) calls reuse it."""
+        check(self.lib.fb_beam_set(self.h, _ptr(beam)))
+
     def beam_convolve(self, beam, field, out):
+        """beam = None: convolve with the beam of the last beam_set / beam_convolve call."""
         check(self.lib.fb_beam_convolve(self.h, _ptr(beam), _ptr(field), _ptr(out)))
 
     def halo_counts(self, delta, nbar, nbar_kind, bias, bias_kind, lognormal, mean_exp, uniforms, counts_out,

@@ -319,6 +319,7 @@ int fb_plan_destroy(fb_plan* p) {
     cudaFree(p->tdense);
     cudaFree(p->work);
     cudaFree(p->aux);
+    cudaFree(p->beam_spec);
     for (int i = 0; i < 6; ++i) cudaFree(p->stage[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(p->ev[i]);
     cudaStreamDestroy(p->stream);

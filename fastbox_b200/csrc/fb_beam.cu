@@ -5,44 +5,84 @@
 // i.e. a LINEAR (zero padded to 2N >= 2N-1) 2-D convolution per frequency channel z, cropped to the
 // first argument's frame: out[x,y] = full[x+st, y+st], st = (N-1)//2.  z is the contiguous batch axis.
 //
-// Three passes over HBM (60 B/cell):
-//   A  y axis, real (N rows, zero padded to 2N) -> N+1 complex, for field and beam      4->8, 4->8
-//   B  x axis: zero padded c2c(2N) of field and beam, product, inverse c2c(2N), crop     8+8->8
-//   C  y axis, N+1 complex -> 2N real, crop, * 1/((2N)^2 norm[z])                        8->4
-// The beam's channel sum norm[z] is the DC bin of its 2-D transform and falls out of pass B.
+// The beam cube of a survey is the same for every field that is convolved with it, so its transform is
+// computed ONCE per plan (fb_beam_set) and kept in HBM, already divided by (2N)^2 norm[z]:
+//     BS[ky][zt][kx][c]   kx = 0..2N-1, ky = 0..N, channel z = 8 zt + c      (16 B/cell, complex64)
+// A convolution is then three passes over HBM (56 B/cell; the x pass does two 2N-point transforms per column
+// instead of three and holds one register array instead of two):
+//   A  y axis, real field rows (zero padded to 2N) -> N+1 complex                        4 -> 8
+//   B  x axis: zero padded c2c(2N), * BS, inverse c2c(2N), crop, in place            8 + 16 -> 8
+//   C  y axis, N+1 complex -> 2N real, crop                                              8 -> 4
+// The intermediate Y lives in the same tiled layout Y[ky][zt][x][c] (c = 0..7): the tile a CTA of pass B
+// transforms is one contiguous 64 N-byte block, and passes A / C touch it in 64-byte rows.
+// norm[z] is a float64 sum over the beam cube (np.sum(beam, axis=(0,1)), beams.py:81).
 #include "fb_launch.h"
 
 namespace fb {
 
-// ---- pass A: y-axis r2c with zero padding.  grid = (N/CZ, N, 2), block = CZ*T(N)
-template <int N, int CZ>
-__global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_r2c(const float* __restrict__ field,
-                                                                 const float* __restrict__ beam,
-                                                                 float2* __restrict__ yf, float2* __restrict__ yb,
-                                                                 const float2* __restrict__ tw) {
+#define FB_BEAM_CT 8                                  // channels per tile of Y / BS
+
+template <int N>
+struct BeamGeom {
+    static constexpr int CT = N < FB_BEAM_CT ? N : FB_BEAM_CT;
+    static constexpr int NZT = N / CT;
+    static constexpr int CZB = CT < 4 ? CT : 4;        // columns per CTA of the x pass
+};
+
+__device__ __forceinline__ size_t beam_tile(int N, int nzt, int ct, int k, int zt, int rows) {
+    return (((size_t)k * nzt + zt) * rows) * ct;       // first element of tile (k, zt): `rows` rows of ct channels
+}
+
+// ---- norm[z] = sum over the N^2 pixels of beam[.,.,z] in float64; inv[z] = 1 / ((2N)^2 norm[z]) --------------
+__global__ void __launch_bounds__(256) k_beam_norm(const float* __restrict__ beam, int N, size_t nrows,
+                                                    double* __restrict__ norm) {
+    const size_t per = (nrows + gridDim.x - 1) / gridDim.x;
+    const size_t r0 = (size_t)blockIdx.x * per, r1 = r0 + per < nrows ? r0 + per : nrows;
+    for (int z = threadIdx.x; z < N; z += blockDim.x) {
+        double a0 = 0.0, a1 = 0.0;
+        size_t r = r0;
+        for (; r + 1 < r1; r += 2) {
+            a0 += (double)__ldg(&beam[r * N + z]);
+            a1 += (double)__ldg(&beam[(r + 1) * N + z]);
+        }
+        if (r < r1) a0 += (double)__ldg(&beam[r * N + z]);
+        if (r1 > r0) atomicAdd(&norm[z], a0 + a1);
+    }
+}
+__global__ void k_beam_inv(const double* __restrict__ norm, int N, float* __restrict__ inv) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z < N) inv[z] = (float)(1.0 / (4.0 * (double)N * (double)N * norm[z]));       // beams.py:87
+}
+
+// ---- pass A: y-axis r2c with zero padding.  grid = (NZT, N), block = CT*T(N) ------------------------------------
+template <int N>
+__global__ void __launch_bounds__(BeamGeom<N>::CT* FftCfg<N>::T) k_beam_y_r2c(const float* __restrict__ src,
+                                                                              float2* __restrict__ Y,
+                                                                              const float2* __restrict__ tw) {
     constexpr int M = N, NF = 2 * N;                 // M complex points represent 2N reals
     using C = FftCfg<M>;
-    constexpr int P = C::P, T = C::T;
+    using G = BeamGeom<N>;
+    constexpr int P = C::P, T = C::T, CT = G::CT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
-    const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
-    const int x = blockIdx.y;
-    const size_t zc = (size_t)blockIdx.x * CZ + col;
-    const float* src = (blockIdx.z ? beam : field) + (size_t)x * N * N + zc;
-    float2* dst = (blockIdx.z ? yb : yf) + (size_t)x * (M + 1) * N + zc;
+    const int col = threadIdx.x % CT, t = threadIdx.x / CT;
+    const int x = blockIdx.y, zt = blockIdx.x;
+    const float* in = src + (size_t)x * N * N + (size_t)zt * CT + col;
     float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int m = t + T * q;                     // rows 2m, 2m+1; zero for rows >= N
-        v[q] = (2 * m + 1 < N) ? make_float2(src[(size_t)(2 * m) * N], src[(size_t)(2 * m + 1) * N])
+        v[q] = (2 * m + 1 < N) ? make_float2(in[(size_t)(2 * m) * N], in[(size_t)(2 * m + 1) * N])
                                : make_float2(0.f, 0.f);
     }
-    ColLayout<CZ> sl{col};
+    ColLayout<CT> sl{col};
     fft_regs<M, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, tw);
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < P; ++q) sm[sl(t + T * q)] = v[q];
     __syncthreads();
+    const size_t kstride = (size_t)G::NZT * N * CT;  // from tile (k, zt) to tile (k+1, zt)
+    float2* dst = Y + beam_tile(N, G::NZT, CT, 0, zt, N) + (size_t)x * CT + col;
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
@@ -50,137 +90,79 @@ __global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_r2c(const float* _
         const float2 zm = cconj(sm[sl((M - k) & (M - 1))]);
         const float2 w = FB_TW(tw, NF, k);      // e^{-2 pi i k / 2N}
         const float2 sp = cadd(zk, zm), df = cmul(csub(zk, zm), w);
-        dst[(size_t)k * N] = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));
-        if (k == 0) dst[(size_t)M * N] = make_float2(zk.x - zk.y, 0.f);
+        dst[(size_t)k * kstride] = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));
+        if (k == 0) dst[(size_t)M * kstride] = make_float2(zk.x - zk.y, 0.f);
     }
 }
 
-// ---- pass B: x axis.  grid = (N/CZ, N+1), block = CZ*T(2N)
-template <int N, int CZ>
-__global__ void __launch_bounds__(CZ * FftCfg<2 * N>::T, 1) k_beam_x(float2* __restrict__ yf,
-                                                                    const float2* __restrict__ yb,
-                                                                    double* __restrict__ norm,
-                                                                    const float2* __restrict__ tw) {
+// ---- pass B: x axis.  grid = (NZT * CT/CZB, N+1), block = CZB*T(2N) ---------------------------------------------
+// SETUP: Y holds the y-transformed BEAM; the 2N-point transform, scaled by inv[z], is stored to BS.
+// else : Y holds the y-transformed field; transform, multiply by BS, inverse transform, crop, store in place.
+template <int N, bool SETUP>
+__global__ void __launch_bounds__(BeamGeom<N>::CZB* FftCfg<2 * N>::T, (BeamGeom<N>::CZB * FftCfg<2 * N>::T <= 512) ? 2 : 1)
+    k_beam_x(float2* __restrict__ Y, float2* __restrict__ BS, const float* __restrict__ inv,
+             const float2* __restrict__ tw) {
     constexpr int NF = 2 * N;
     using C = FftCfg<NF>;
-    constexpr int P = C::P, T = C::T;
+    using G = BeamGeom<N>;
+    constexpr int P = C::P, T = C::T, CT = G::CT, CZ = G::CZB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
     const int ky = blockIdx.y;
-    const size_t zc = (size_t)blockIdx.x * CZ + col;
-    const size_t plane = (size_t)(N + 1) * N;
-    float2* f = yf + (size_t)ky * N + zc;
-    const float2* b = yb + (size_t)ky * N + zc;
-    float2 vf[P], vb[P];
+    const int zt = blockIdx.x / (CT / CZ), c = (blockIdx.x % (CT / CZ)) * CZ + col;
+    float2* y = Y + beam_tile(N, G::NZT, CT, ky, zt, N) + c;
+    float2* bs = BS + beam_tile(N, G::NZT, CT, ky, zt, NF) + c;
+    float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int x = t + T * q;                     // zero padding for x >= N
-        vf[q] = x < N ? f[(size_t)x * plane] : make_float2(0.f, 0.f);
-        vb[q] = x < N ? b[(size_t)x * plane] : make_float2(0.f, 0.f);
+        v[q] = x < N ? y[(size_t)x * CT] : make_float2(0.f, 0.f);
     }
     ColLayout<CZ> sl{col};
-    fft_regs<NF, P, C::R1, C::R2, C::R3, -1>(vf, t, sm, sl, tw);
-    __syncthreads();
-    fft_regs<NF, P, C::R1, C::R2, C::R3, -1>(vb, t, sm, sl, tw);
-    __syncthreads();
-    if (ky == 0 && t == 0) norm[zc] = (double)vb[0].x;           // DC bin = sum_xy beam (beams.py:81)
-#pragma unroll
-    for (int q = 0; q < P; ++q) vf[q] = cmul(vf[q], vb[q]);
-    fft_regs<NF, P, C::R1, C::R2, C::R3, +1>(vf, t, sm, sl, tw);
-    constexpr int st = (N - 1) / 2;                  // 'same' crop w.r.t. the first argument
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int xo = t + T * q - st;
-        if (xo >= 0 && xo < N) f[(size_t)xo * plane] = vf[q];
-    }
-}
-
-// ---- pass B, role-split variant for large boxes.  grid = (N/CZ, N+1), block = 2*CZ*T(2N).
-// The first CZ*T threads transform the field columns, the other CZ*T the beam columns (whole warps per
-// role), so a thread holds 16 points instead of 32 and a 1024-thread CTA fits an SM (32 warps instead
-// of 16 for the two forward transforms).  The beam spectrum crosses to the field threads through the
-// exchange buffer; the beam warps then only keep the barriers of the inverse transform company.
-// Measured SLOWER than k_beam_x at 1024^3 (one 1024-thread CTA per SM serialises its load / transform /
-// store phases); kept as an opt-in experiment (FB_BEAM_SPLIT=1) and covered by the parity tests.
-template <int N, int CZ>
-__global__ void __launch_bounds__(2 * CZ * FftCfg<2 * N>::T, 1) k_beam_x_split(float2* __restrict__ yf,
-                                                                              const float2* __restrict__ yb,
-                                                                              double* __restrict__ norm,
-                                                                              const float2* __restrict__ tw) {
-    constexpr int NF = 2 * N;
-    using C = FftCfg<NF>;
-    constexpr int P = C::P, T = C::T;
-    static_assert((CZ * T) % 32 == 0, "roles must own whole warps");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* sm = reinterpret_cast<float2*>(smem_raw);
-    const int role = threadIdx.x / (CZ * T);             // 0 field, 1 beam
-    const int r = threadIdx.x - role * (CZ * T);
-    const int col = r % CZ, t = r / CZ;
-    const int ky = blockIdx.y;
-    const size_t zc = (size_t)blockIdx.x * CZ + col;
-    const size_t plane = (size_t)(N + 1) * N;
-    float2* f = yf + (size_t)ky * N + zc;
-    const float2* src = (role ? yb : yf) + (size_t)ky * N + zc;
-    float2 v[P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int x = t + T * q;                         // zero padding for x >= N
-        v[q] = x < N ? src[(size_t)x * plane] : make_float2(0.f, 0.f);
-    }
-    ColLayout<2 * CZ> sl{role * CZ + col};
     fft_regs<NF, P, C::R1, C::R2, C::R3, -1>(v, t, sm, sl, tw);
-    __syncthreads();
-    if (role) {
-        if (ky == 0 && t == 0) norm[zc] = (double)v[0].x;            // DC bin = sum_xy beam (beams.py:81)
-        fft_store_natural<NF, P>(v, t, sm, sl);
-    }
-    __syncthreads();
-    if (!role) {
-        ColLayout<2 * CZ> sb{CZ + col};
-        float2 vb[P];
-        fft_exchange_read<NF, P>(vb, t, sm, sb);
+    if constexpr (SETUP) {
+        const float s = __ldg(&inv[zt * CT + c]);
 #pragma unroll
-        for (int q = 0; q < P; ++q) v[q] = cmul(v[q], vb[q]);
-    }
-    __syncthreads();
-    if (role) {
-        fft_regs_barriers_only<C::R2, C::R3>();
-        return;
-    }
-    fft_regs<NF, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, tw);
-    constexpr int st = (N - 1) / 2;                      // 'same' crop w.r.t. the first argument
+        for (int q = 0; q < P; ++q) bs[(size_t)(t + T * q) * CT] = make_float2(v[q].x * s, v[q].y * s);
+    } else {
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int xo = t + T * q - st;
-        if (xo >= 0 && xo < N) f[(size_t)xo * plane] = v[q];
+        for (int q = 0; q < P; ++q) v[q] = cmul(v[q], __ldg(&bs[(size_t)(t + T * q) * CT]));
+        __syncthreads();                             // the exchange buffer is reused
+        fft_regs<NF, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, tw);
+        constexpr int st = (N - 1) / 2;              // 'same' crop w.r.t. the first argument
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int xo = t + T * q - st;
+            if (xo >= 0 && xo < N) y[(size_t)xo * CT] = v[q];
+        }
     }
 }
 
-// ---- pass C: y axis c2r with crop and normalisation.  grid = (N/CZ, N), block = CZ*T(N)
-template <int N, int CZ>
-__global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_c2r(const float2* __restrict__ yf,
-                                                                 const double* __restrict__ norm,
-                                                                 float* __restrict__ out,
-                                                                 const float2* __restrict__ tw) {
+// ---- pass C: y axis c2r with crop (the normalisation sits in BS).  grid = (NZT, N), block = CT*T(N) -------------
+template <int N>
+__global__ void __launch_bounds__(BeamGeom<N>::CT* FftCfg<N>::T) k_beam_y_c2r(const float2* __restrict__ Y,
+                                                                              float* __restrict__ out,
+                                                                              const float2* __restrict__ tw) {
     constexpr int M = N, NF = 2 * N;
     using C = FftCfg<M>;
-    constexpr int P = C::P, T = C::T;
+    using G = BeamGeom<N>;
+    constexpr int P = C::P, T = C::T, CT = G::CT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sm = reinterpret_cast<float2*>(smem_raw);
-    const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
-    const int x = blockIdx.y;
-    const size_t zc = (size_t)blockIdx.x * CZ + col;
-    const float2* src = yf + (size_t)x * (M + 1) * N + zc;
-    ColLayout<CZ> sl{col};
+    const int col = threadIdx.x % CT, t = threadIdx.x / CT;
+    const int x = blockIdx.y, zt = blockIdx.x;
+    const size_t kstride = (size_t)G::NZT * N * CT;
+    const float2* src = Y + beam_tile(N, G::NZT, CT, 0, zt, N) + (size_t)x * CT + col;
+    ColLayout<CT> sl{col};
     float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        v[q] = src[(size_t)(t + T * q) * N];
+        v[q] = src[(size_t)(t + T * q) * kstride];
         sm[sl(t + T * q)] = v[q];
     }
     float2 xnyq = make_float2(0.f, 0.f);
-    if (t == 0) xnyq = src[(size_t)M * N];
+    if (t == 0) xnyq = src[(size_t)M * kstride];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < P; ++q) {
@@ -194,108 +176,129 @@ __global__ void __launch_bounds__(CZ * FftCfg<N>::T) k_beam_y_c2r(const float2* 
     }
     if constexpr (C::R2 > 1) __syncthreads();
     fft_regs<M, P, C::R1, C::R2, C::R3, +1>(v, t, sm, sl, tw);
-    const float scale = (float)(1.0 / ((double)NF * (double)NF * norm[zc]));      // beams.py:87
     constexpr int st = (N - 1) / 2;
-    float* dst = out + (size_t)x * N * N + zc;
+    float* dst = out + (size_t)x * N * N + (size_t)zt * CT + col;
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int m = t + T * q;
         const int y0 = 2 * m - st, y1 = 2 * m + 1 - st;
-        if (y0 >= 0 && y0 < N) dst[(size_t)y0 * N] = v[q].x * scale;
-        if (y1 >= 0 && y1 < N) dst[(size_t)y1 * N] = v[q].y * scale;
+        if (y0 >= 0 && y0 < N) dst[(size_t)y0 * N] = v[q].x;
+        if (y1 >= 0 && y1 < N) dst[(size_t)y1 * N] = v[q].y;
     }
 }
 
-template <int N, int CZA, int CZB>
-static int beam_run_cz(fb_plan* p, const float* beam, const float* field, float* out, float2* yf, float2* yb,
-                       double* norm) {
-    {
-        auto kern = k_beam_y_r2c<N, CZA>;
-        const size_t smem = (size_t)(N + N / 16) * CZA * sizeof(float2);
-        if (set_smem(kern, smem)) return -2;
-        kern<<<dim3(N / CZA, N, 2), CZA * FftCfg<N>::T, smem, p->stream>>>(field, beam, yf, yb, p->tw);
-        FB_LAUNCH_CHECK();
-    }
-    if constexpr (N >= 512) {
-        if (env_int("FB_BEAM_SPLIT", 0)) {          // measured slower at 1024^3 (32.7 vs 28.8 ms): opt-in
-            auto kern = k_beam_x_split<N, CZB>;
-            const size_t smem = (size_t)(2 * N + 2 * N / 16) * 2 * CZB * sizeof(float2);
-            if (set_smem(kern, smem)) return -2;
-            kern<<<dim3(N / CZB, N + 1), 2 * CZB * FftCfg<2 * N>::T, smem, p->stream>>>(yf, yb, norm, p->tw);
-            FB_LAUNCH_CHECK();
-        } else {
-            auto kern = k_beam_x<N, CZB>;
-            const size_t smem = (size_t)(2 * N + 2 * N / 16) * CZB * sizeof(float2);
-            if (set_smem(kern, smem)) return -2;
-            kern<<<dim3(N / CZB, N + 1), CZB * FftCfg<2 * N>::T, smem, p->stream>>>(yf, yb, norm, p->tw);
-            FB_LAUNCH_CHECK();
-        }
-    } else {
-        auto kern = k_beam_x<N, CZB>;
-        const size_t smem = (size_t)(2 * N + 2 * N / 16) * CZB * sizeof(float2);
-        if (set_smem(kern, smem)) return -2;
-        kern<<<dim3(N / CZB, N + 1), CZB * FftCfg<2 * N>::T, smem, p->stream>>>(yf, yb, norm, p->tw);
-        FB_LAUNCH_CHECK();
-    }
-    {
-        auto kern = k_beam_y_c2r<N, CZA>;
-        const size_t smem = (size_t)(N + N / 16) * CZA * sizeof(float2);
-        if (set_smem(kern, smem)) return -2;
-        kern<<<dim3(N / CZA, N), CZA * FftCfg<N>::T, smem, p->stream>>>(yf, norm, out, p->tw);
-        FB_LAUNCH_CHECK();
-    }
+template <int N>
+static int beam_pass_a(fb_plan* p, const float* src, float2* Y) {
+    using G = BeamGeom<N>;
+    auto kern = k_beam_y_r2c<N>;
+    const size_t smem = (size_t)(N + N / 16) * G::CT * sizeof(float2);
+    if (set_smem(kern, smem)) return -2;
+    kern<<<dim3(G::NZT, N), G::CT * FftCfg<N>::T, smem, p->stream>>>(src, Y, p->tw);
+    FB_LAUNCH_CHECK();
     return 0;
 }
 
-// columns (z) per CTA: y passes CZA, x pass CZB.  Large boxes take narrower tiles so that two or
-// three CTAs share an SM and their load / transform / store phases overlap.
-template <int N>
-static int beam_run(fb_plan* p, const float* beam, const float* field, float* out, float2* yf, float2* yb,
-                    double* norm) {
-    if constexpr (N >= 512) {
-        const int cza = env_int("FB_BEAM_CZA", 8), czb = env_int("FB_BEAM_CZB", 4);
-        if (cza == 8 && czb == 2) return beam_run_cz<N, 8, 2>(p, beam, field, out, yf, yb, norm);
-        if (cza == 8) return beam_run_cz<N, 8, 4>(p, beam, field, out, yf, yb, norm);
-        if (czb == 2) return beam_run_cz<N, 16, 2>(p, beam, field, out, yf, yb, norm);
-        return beam_run_cz<N, 16, 4>(p, beam, field, out, yf, yb, norm);
-    } else {
-        constexpr int CZA = N >= 16 ? 16 : N;
-        constexpr int CZB = N >= 4 ? 4 : N;
-        return beam_run_cz<N, CZA, CZB>(p, beam, field, out, yf, yb, norm);
-    }
+template <int N, bool SETUP>
+static int beam_pass_b(fb_plan* p, float2* Y, float2* BS, const float* inv) {
+    using G = BeamGeom<N>;
+    auto kern = k_beam_x<N, SETUP>;
+    const size_t smem = (size_t)(2 * N + 2 * N / 16) * G::CZB * sizeof(float2);
+    if (set_smem(kern, smem)) return -2;
+    kern<<<dim3(G::NZT * (G::CT / G::CZB), N + 1), G::CZB * FftCfg<2 * N>::T, smem, p->stream>>>(Y, BS, inv, p->tw);
+    FB_LAUNCH_CHECK();
+    return 0;
 }
+
+template <int N>
+static int beam_set(fb_plan* p, const float* beam, float2* Y, float2* BS, double* norm, float* inv) {
+    FB_CUDA(cudaMemsetAsync(norm, 0, (size_t)N * sizeof(double), p->stream));
+    const size_t nrows = (size_t)N * N;
+    const unsigned grid = (unsigned)((size_t)p->sm_count * 8 < nrows ? (size_t)p->sm_count * 8 : nrows);
+    k_beam_norm<<<grid, 256, 0, p->stream>>>(beam, N, nrows, norm);
+    FB_LAUNCH_CHECK();
+    k_beam_inv<<<(N + 255) / 256, 256, 0, p->stream>>>(norm, N, inv);
+    FB_LAUNCH_CHECK();
+    if (int rc = beam_pass_a<N>(p, beam, Y)) return rc;
+    return beam_pass_b<N, true>(p, Y, BS, inv);
+}
+
+template <int N>
+static int beam_run(fb_plan* p, const float* field, float* out, float2* Y, float2* BS) {
+    if (int rc = beam_pass_a<N>(p, field, Y)) return rc;
+    if (int rc = beam_pass_b<N, false>(p, Y, BS, nullptr)) return rc;
+    using G = BeamGeom<N>;
+    auto kern = k_beam_y_c2r<N>;
+    const size_t smem = (size_t)(N + N / 16) * G::CT * sizeof(float2);
+    if (set_smem(kern, smem)) return -2;
+    kern<<<dim3(G::NZT, N), G::CT * FftCfg<N>::T, smem, p->stream>>>(Y, out, p->tw);
+    FB_LAUNCH_CHECK();
+    return 0;
+}
+
+static size_t beam_y_elems(int N) { return (size_t)N * (N + 1) * N; }
 
 }  // namespace fb
 
 using namespace fb;
 
+#define FB_BEAM_DISPATCH(N_, CALL)                     \
+    switch (N_) {                                      \
+        case 8: { constexpr int NN = 8; rc = CALL; } break;       \
+        case 16: { constexpr int NN = 16; rc = CALL; } break;     \
+        case 32: { constexpr int NN = 32; rc = CALL; } break;     \
+        case 64: { constexpr int NN = 64; rc = CALL; } break;     \
+        case 128: { constexpr int NN = 128; rc = CALL; } break;   \
+        case 256: { constexpr int NN = 256; rc = CALL; } break;   \
+        case 512: { constexpr int NN = 512; rc = CALL; } break;   \
+        case 1024: { constexpr int NN = 1024; rc = CALL; } break; \
+        default: set_error("beam convolution: unsupported N=%d", N_); return -1; \
+    }
+
+extern "C" int fb_beam_set(fb_plan* p, const float* beam) {
+    FB_CUDA(cudaSetDevice(p->device));
+    const int N = p->N;
+    FB_CHECK(beam != nullptr, "fb_beam_set: NULL beam");
+    FB_CHECK(N >= 8 && N <= 1024, "fb_beam_set: N=%d not supported (8..1024; padded transform is 2N <= 2048)", N);
+    const size_t n3 = (size_t)N * N * N, ny = beam_y_elems(N);
+    const void* db = nullptr;
+    if (stage_in(p, 0, beam, n3 * sizeof(float), &db)) return -2;
+    const size_t bs_bytes = 2 * ny * sizeof(float2) + (size_t)N * (sizeof(double) + sizeof(float));
+    p->beam_ready = 0;
+    if (p->beam_spec_bytes < bs_bytes) {
+        if (p->beam_spec) FB_CUDA(cudaFree(p->beam_spec));
+        p->beam_spec = nullptr;
+        p->beam_spec_bytes = 0;
+        FB_CUDA(cudaMalloc(&p->beam_spec, bs_bytes));
+        p->beam_spec_bytes = bs_bytes;
+    }
+    if (ensure_aux(p, ny * sizeof(float2))) return -2;
+    float2* BS = (float2*)p->beam_spec;
+    double* norm = (double*)(BS + 2 * ny);
+    float* inv = (float*)(norm + N);
+    int rc = 0;
+    FB_BEAM_DISPATCH(N, (beam_set<NN>(p, (const float*)db, (float2*)p->aux, BS, norm, inv)));
+    if (rc) return rc;
+    p->beam_ready = 1;
+    return 0;
+}
+
 extern "C" int fb_beam_convolve(fb_plan* p, const float* beam, const float* field, float* out) {
     FB_CUDA(cudaSetDevice(p->device));
     const int N = p->N;
-    FB_CHECK(beam && field && out, "fb_beam_convolve: NULL buffer");
+    FB_CHECK(field && out, "fb_beam_convolve: NULL buffer");
     FB_CHECK(N >= 8 && N <= 1024, "fb_beam_convolve: N=%d not supported (8..1024; padded transform is 2N <= 2048)", N);
-    const size_t n3 = (size_t)N * N * N, ny = (size_t)N * (N + 1) * N;
-    const void *db = nullptr, *df = nullptr;
+    if (beam != nullptr) {
+        if (int rc = fb_beam_set(p, beam)) return rc;
+    }
+    FB_CHECK(p->beam_ready, "fb_beam_convolve: no beam (pass a beam cube or call fb_beam_set first)");
+    const size_t n3 = (size_t)N * N * N, ny = beam_y_elems(N);
+    const void* df = nullptr;
     void* dout = nullptr;
-    if (stage_in(p, 0, beam, n3 * sizeof(float), &db)) return -2;
     if (stage_in(p, 1, field, n3 * sizeof(float), &df)) return -2;
     if (stage_out_begin(p, 2, out, n3 * sizeof(float), &dout)) return -2;
-    if (ensure_aux(p, 2 * ny * sizeof(float2) + (size_t)N * sizeof(double))) return -2;
-    float2* yf = (float2*)p->aux;
-    float2* yb = yf + ny;
-    double* norm = (double*)(yb + ny);
+    if (ensure_aux(p, ny * sizeof(float2))) return -2;
     int rc = 0;
-    switch (N) {
-        case 8: rc = beam_run<8>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 16: rc = beam_run<16>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 32: rc = beam_run<32>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 64: rc = beam_run<64>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 128: rc = beam_run<128>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 256: rc = beam_run<256>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 512: rc = beam_run<512>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        case 1024: rc = beam_run<1024>(p, (const float*)db, (const float*)df, (float*)dout, yf, yb, norm); break;
-        default: set_error("fb_beam_convolve: unsupported N=%d", N); return -1;
-    }
+    FB_BEAM_DISPATCH(N, (beam_run<NN>(p, (const float*)df, (float*)dout, (float2*)p->aux, (float2*)p->beam_spec)));
     if (rc) return rc;
     if (stage_out_end(p, 2, out, n3 * sizeof(float))) return -2;
     return 0;

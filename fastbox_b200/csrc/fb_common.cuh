@@ -122,6 +122,9 @@ struct fb_plan {
     // beam / misc workspaces
     void* aux;
     size_t aux_bytes;
+    void* beam_spec;        // fb_beam_set: normalised 2-D beam spectrum BS[ky][zt][kx][c] + norm[z] + inv[z]
+    size_t beam_spec_bytes;
+    int beam_ready;
     cudaEvent_t ev[8];
     float last_ms[8];
     int n_last;

@@ -165,6 +165,12 @@ int fb_rsd_remap(fb_plan* plan, const float* delta, const float* vel_z, const fl
                  double Hz, float* out);
 
 /* ---- beam convolution: beams.py:81-87 ----------------------------------------- */
+/* out = fftconvolve(beam, field, mode='same', axes=[0,1]) / sum_xy beam  per channel z.
+ * fb_beam_set transforms the beam cube once (float64 channel sums, zero-padded 2-D spectrum divided by
+ * (2N)^2 norm[z], 16 B/cell of device memory held by the plan until the next fb_beam_set / fb_plan_destroy);
+ * fb_beam_convolve with beam = NULL reuses it, with a beam cube it calls fb_beam_set first (the reference's
+ * call: the beam is re-derived on every convolve_fft, beams.py:79).  N <= 1024.                                */
+int fb_beam_set(fb_plan* plan, const float* beam);
 int fb_beam_convolve(fb_plan* plan, const float* beam, const float* field, float* out);
 
 /* ---- halo counts: halos.py:91-117 ---------------------------------------------- */

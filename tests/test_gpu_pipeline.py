@@ -289,8 +289,11 @@ def test_beam_convolve_vs_oracle(gpu, N):
     plan.close()
 
 
-def test_beam_convolve_large_box_variants(gpu, monkeypatch):
-    """N >= 512 takes the role-split x pass and narrower y tiles: every variant against scipy on single channels."""
+def test_beam_convolve_large_box_and_cached_spectrum(gpu):
+    """
+    N = 512 (2N = 1024-point x transforms, 8-channel tiles): single channels against scipy; the cached beam
+    spectrum (fb_beam_set once, beam = NULL afterwards) gives bit-identical results, and a second beam replaces it.
+    """
     import scipy.signal
     N = 512
     rng = np.random.default_rng(5)
@@ -300,19 +303,29 @@ def test_beam_convolve_large_box_variants(gpu, monkeypatch):
     beam = (np.exp(-0.5 * (x[:, None, None] ** 2 + (x[None, :, None] - 0.7) ** 2) / s[None, None, :] ** 2)
             * (1 + 0.1 * np.cos(x[:, None, None]))).astype(np.float32)
     plan = _lib.Plan(N, 1e3, 1e3, 1e3)
-    outs = {}
-    for split, cza in ((1, 8), (0, 16), (1, 16)):
-        monkeypatch.setenv("FB_BEAM_SPLIT", str(split))
-        monkeypatch.setenv("FB_BEAM_CZA", str(cza))
-        out = np.empty((N, N, N), np.float32)
-        plan.beam_convolve(beam, field, out)
-        outs[(split, cza)] = out
+    out = np.empty((N, N, N), np.float32)
+    plan.beam_convolve(beam, field, out)
     for z in (0, 201, N - 1):
         b2, f2 = beam[:, :, z].astype(np.float64), field[:, :, z].astype(np.float64)
         ref = scipy.signal.fftconvolve(b2, f2, mode='same') / b2.sum()         # beams.py:81-87, one channel
-        for out in outs.values():
-            assert rel_l2(out[:, :, z], ref) < TOL
-    assert np.array_equal(outs[(1, 8)], outs[(1, 16)])
+        assert rel_l2(out[:, :, z], ref) < TOL
+    out2 = np.empty((N, N, N), np.float32)
+    plan.beam_convolve(None, field, out2)                                      # cached spectrum
+    assert np.array_equal(out, out2)
+    beam_b = np.ascontiguousarray(beam[::-1] * 3.0)
+    plan.beam_set(beam_b)
+    plan.beam_convolve(None, field, out2)
+    z = 77
+    b2, f2 = beam_b[:, :, z].astype(np.float64), field[:, :, z].astype(np.float64)
+    assert rel_l2(out2[:, :, z], scipy.signal.fftconvolve(b2, f2, mode='same') / b2.sum()) < TOL
+    plan.close()
+
+
+def test_beam_convolve_needs_a_beam(gpu):
+    plan = _lib.Plan(16, 1e2, 1e2, 1e2)
+    f = np.zeros((16, 16, 16), np.float32)
+    with pytest.raises(_lib.FastBoxError):
+        plan.beam_convolve(None, f, np.empty_like(f))
     plan.close()
 
 

@@ -86,7 +86,9 @@ def main():
         s = 1.5 + 4.0 * np.arange(N) / N
         beam = plan.upload_f32(np.exp(-0.5 * (x[:, None, None] ** 2 + x[None, :, None] ** 2) / s[None, None, :] ** 2)
                                .astype(np.float32)) if N <= 512 else f3
-        add("beam convolve_fft  [a11]", 60, timed(plan, lambda: plan.beam_convolve(beam, field, out), reps=3))
+        add("beam spectrum set-up (once per beam)  [a11]", 44, timed(plan, lambda: plan.beam_set(beam), reps=2))
+        add("beam convolve_fft, cached beam spectrum  [a11]", 56,
+            timed(plan, lambda: plan.beam_convolve(None, field, out), reps=3))
     u = plan.upload(np.random.default_rng(1).random(n3))
     counts = plan.alloc(n3 * 4)
     nbar = np.array([1e-3], np.float32)
