@@ -252,6 +252,8 @@ def run_single(args):
     # ---- e2e: host (pinned) buffers through the same C-ABI call
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e, tuning runs only)")
         h_re = plan.host_alloc((n3,), np.float32)
         h_im = plan.host_alloc((n3,), np.float32)
         h_field = plan.host_alloc((n3,), np.float32)
@@ -711,6 +713,7 @@ def main():
                     choices=["headline", "lognormal_rsd_512", "filter_beam_poles_1024", "halos_cross_1024"],
                     help="BASELINE.json configs[1..3] as stage-by-stage pipelines (one JSON line each)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs: skip the host-buffer leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -33,11 +33,12 @@ static int launch_cols_t(fb_plan* p, const SlabView& vin, const SlabView& vout, 
     using G = ColGeom<N, CZ>;
     dim3 grid(N / CZ, nplanes);
     const bool slab = vin.ny != 0 || vout.ny != 0;
+    const int pf = env_int("FB_COLS_PF", FB_COLS_PF_DEFAULT);
 #define FB_COLS_LAUNCH(SIGN_, SLAB_)                                                         \
     {                                                                                        \
         auto kern = k_cols_c2c<N, CZ, SIGN_, SLAB_>;                                         \
         if (set_smem(kern, G::SMEM)) return -2;                                              \
-        kern<<<grid, G::THREADS, G::SMEM, st>>>(vin.base[0], vout.base[0], vin, vout, p->tw); \
+        kern<<<grid, G::THREADS, G::SMEM, st>>>(vin.base[0], vout.base[0], vin, vout, p->tw, pf); \
     }
     if (sign < 0) {
         if (slab) FB_COLS_LAUNCH(-1, true) else FB_COLS_LAUNCH(-1, false)
@@ -130,8 +131,6 @@ static int launch_x_n(fb_plan* p, const XArgs& a, bool inv, int dflt) {
 }
 
 static int launch_x(fb_plan* p, const XArgs& a, bool inv) {
-    // plain layouts on large grids: persistent TMA-pipelined kernels (fb_x_tma.cu); FB_X_TMA=0 keeps the per-thread ones
-    if (env_int("FB_X_TMA", FB_X_TMA_DEFAULT) && x_tma_available(p, a, inv)) return launch_x_tma(p, a, inv);
     switch (p->N) {
         case 8: return launch_x_t<8, 32>(p, a, inv);
         case 16: return launch_x_t<16, 32>(p, a, inv);

@@ -50,8 +50,13 @@ struct fb_dist_state {
     int xmode;
     float2* send;                   // xmode 1: [chunk][dest][plane][y'][z] staging, same size as the work array
     size_t send_bytes;
+    //   2 = as 1, but a small high-priority copy kernel (k_dist_push: a few CTAs per peer, 16-byte loads, 16-byte
+    //       peer stores in fully contiguous 512-byte warp requests) pushes the blocks: NVLink sees large
+    //       requests instead of the 64-byte rows of the y pass tiles, and the k-space kernels keep the SMs.
     cudaStream_t cps[FB_MAX_RANKS];
     cudaEvent_t ev_y[FB_DIST_MAX_CHUNKS], ev_cp[FB_MAX_RANKS];
+    cudaStream_t push;              // xmode 2: highest-priority stream of the copy kernel
+    int push_ctas;                  // CTAs per peer
 };
 
 namespace fb {
@@ -70,6 +75,29 @@ struct PeerBlocks {
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// xmode 2: contiguous blocks local -> peer, blockIdx.y = peer slot.  Eight independent 16-byte loads per thread
+// in flight, then eight 16-byte stores; a warp request covers 512 contiguous bytes on both sides.
+struct PushArgs {
+    const uint4* src[FB_MAX_RANKS];
+    uint4* dst[FB_MAX_RANKS];
+    size_t n16;
+};
+__global__ void __launch_bounds__(512) k_dist_push(const PushArgs a) {
+    const uint4* __restrict__ s = a.src[blockIdx.y];
+    uint4* __restrict__ d = a.dst[blockIdx.y];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int UN = 8;
+    for (; i + (UN - 1) * stride < a.n16; i += UN * stride) {
+        uint4 v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) v[u] = __ldcs(s + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) d[i + u * stride] = v[u];
+    }
+    for (; i < a.n16; i += stride) d[i] = __ldcs(s + i);
+}
 
 // flags[d][rank] = epoch on every peer d: "everything this rank stores for step `epoch` is visible"
 __global__ void k_dist_signal(PeerBlocks peers, size_t off_flags, int rank, int world, unsigned long long epoch) {
@@ -158,6 +186,7 @@ void dist_destroy(fb_plan* p) {
         if (d->ipc_opened[r]) cudaIpcCloseMemHandle(d->peer[r]);
     if (d->block) cudaFree(d->block);
     if (d->aux) cudaStreamDestroy(d->aux);
+    if (d->push) cudaStreamDestroy(d->push);
     for (int c = 0; c < FB_DIST_MAX_CHUNKS; ++c)
         if (d->ev_rows[c]) cudaEventDestroy(d->ev_rows[c]);
     if (d->ev_start) cudaEventDestroy(d->ev_start);
@@ -282,6 +311,13 @@ int fb_dist_init(fb_plan* p, int rank, int world, int with_forward) {
         FB_CUDA(cudaEventCreateWithFlags(&d->ev_cp[r], cudaEventDisableTiming));
     }
     for (int c = 0; c < FB_DIST_MAX_CHUNKS; ++c) FB_CUDA(cudaEventCreateWithFlags(&d->ev_y[c], cudaEventDisableTiming));
+    {
+        int lo = 0, hi = 0;
+        FB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        FB_CUDA(cudaStreamCreateWithPriority(&d->push, cudaStreamNonBlocking, hi));
+        const int dflt = world > 1 ? (48 / (world - 1) > 4 ? 48 / (world - 1) : 4) : 1;
+        d->push_ctas = env_int("FB_DIST_PUSH_CTAS", dflt);
+    }
     d->cz_cols = env_int("FB_DIST_CZ", N >= 2048 ? 8 : 0);
     d->timeout_s = (double)env_int("FB_DIST_TIMEOUT_S", 20);
     d->peer[rank] = d->block;
@@ -422,6 +458,30 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                         reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
                 if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), vout, npl, +1, p->stream, d->cz_cols))
                     return -3;
+            } else if (d->xmode == 2) {
+                // y pass into local per-destination blocks (this rank's own block goes straight to its receive
+                // buffer), then the copy kernel pushes the other blocks on the high-priority stream
+                float2* send_c = d->send + (size_t)pl0 * N * N;
+                SlabView vsend = block_view(send_c, ny, npl, N);
+                vsend.base[d->rank] =
+                    reinterpret_cast<float2*>(d->block + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
+                if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), vsend, npl, +1, p->stream, 0)) return -3;
+                FB_CUDA(cudaEventRecord(d->ev_y[c], p->stream));
+                if (d->world > 1) {
+                    const size_t blk = (size_t)npl * ny * N;
+                    PushArgs pa;
+                    memset(&pa, 0, sizeof(pa));
+                    pa.n16 = blk * sizeof(float2) / sizeof(uint4);
+                    for (int k = 0; k < d->world - 1; ++k) {
+                        const int r = (d->rank + 1 + k) % d->world;
+                        pa.src[k] = reinterpret_cast<const uint4*>(send_c + (size_t)r * blk);
+                        pa.dst[k] = reinterpret_cast<uint4*>(reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) +
+                                                             (size_t)(p->a0 + pl0) * ny * N);
+                    }
+                    FB_CUDA(cudaStreamWaitEvent(d->push, d->ev_y[c], 0));
+                    k_dist_push<<<dim3(d->push_ctas, d->world - 1), 512, 0, d->push>>>(pa);
+                    FB_LAUNCH_CHECK();
+                }
             } else {
                 // y pass into local per-destination blocks, then one copy-engine transfer per peer
                 float2* send_c = d->send + (size_t)pl0 * N * N;
@@ -439,11 +499,14 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                 }
             }
         }
-        if (d->xmode != 0) {
+        if (d->xmode == 1) {
             for (int r = 0; r < d->world; ++r) {
                 FB_CUDA(cudaEventRecord(d->ev_cp[r], d->cps[r]));
                 FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[r], 0));
             }
+        } else if (d->xmode == 2) {
+            FB_CUDA(cudaEventRecord(d->ev_cp[0], d->push));
+            FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[0], 0));
         }
         if (pk) {
             k_pk_share<<<p->nedges + 1, 32, 0, p->stream>>>(p->h_count, p->h_sums, peer_blocks(d),

@@ -21,10 +21,15 @@ int launch_cols_tma(fb_plan* p, const float2* in, float2* out, int nplanes, int 
 #ifndef FB_COLS_TMA_DEFAULT
 #define FB_COLS_TMA_DEFAULT 1
 #endif
-bool x_tma_available(const fb_plan* p, const XArgs& a, bool inverse);
-int launch_x_tma(fb_plan* p, const XArgs& a, bool inverse);
-#ifndef FB_X_TMA_DEFAULT
-#define FB_X_TMA_DEFAULT 0
+// L2 prefetch distance in CTAs (0 = off): a CTA asks L2 for the input of the CTA that many blocks ahead.
+// Measured at 1024^3 (profiles/README.md): first pass 3.06 -> 2.79 ms for any distance in 37..185 (worse beyond
+// 300: the lines are evicted before use), per-thread y pass 1.68 -> 1.54 ms at 74; the same trick on the x
+// passes (one line per thread, rows a whole plane apart) cost 0.6 ms and was removed.
+#ifndef FB_ROWS_PF_DEFAULT
+#define FB_ROWS_PF_DEFAULT 74
+#endif
+#ifndef FB_COLS_PF_DEFAULT
+#define FB_COLS_PF_DEFAULT 74
 #endif
 int launch_x_c2r(fb_plan* p, const XArgs& a);
 int launch_x_r2c(fb_plan* p, const XArgs& a);

@@ -86,18 +86,23 @@ __global__ void __launch_bounds__(256) k_f32_to_f64(const float* __restrict__ sr
 }
 
 // ---------------------------------------------------------------------------
-// Redshift-space remap, one CTA per line of sight (box.py:412-437).
+// Redshift-space remap (box.py:412-437), several lines of sight per CTA, software pipelined.
 //   s_l = z_l - (v_z + v_nl)_l / H, wrapped periodically into [z_0, z_{N-1});   out_l = linear
 //   re-grid of the scattered samples (s, delta) onto z  (scipy griddata 1-D = argsort +
 //   interp1d(linear, fill_value)): out(z) = y_lo + (y_hi-y_lo)/(x_hi-x_lo) (z-x_lo) with
 //   x_lo = largest sample < z, x_hi = smallest sample >= z; fill = (delta_0+delta_{N-1})/2 outside
 //   [min s, max s].
-// No sort is needed.  Every sample is dropped into the grid cell [z_c, z_{c+1}) that contains it,
-// keeping per cell the largest and the smallest sample (64-bit shared-memory atomic max / min on an
-// order-preserving key that carries the sample index in its low bits).  The bracket of output z_l is
-// then the max of the nearest non-empty cell below l and the min of the nearest non-empty cell at or
-// above l -- exactly the pair the sorted search returns -- found in O(1) expected steps.
-// Coordinates in float64 like the reference.
+// No sort is needed.  Every sample is dropped into the grid cell that contains it, keeping per cell the
+// largest and the smallest sample (native 32-bit shared-memory atomic max / min on a key = position inside the
+// cell | sample index).  The bracket of output z_l is then the max of the nearest non-empty cell below l and
+// the min of the nearest non-empty cell at or above l -- the pair the sorted search returns -- found in O(1)
+// expected steps.
+// Positions are carried in CELL UNITS: one float64 multiply-add, floor and multiply give the wrapped position
+// p = frac((z_l - z_0)/length - v/(H length)) (N-1) to 1e-16 of the box; it is then split into the integer
+// cell and a float32 fraction in [0, 1) (6e-8 of a cell; a fraction that rounds to 1 moves to the next cell,
+// so a sample that sits on a grid point -- v = 0 -- is found there exactly).  The interpolation weight
+// ((l - c_lo) - f_lo) / ((c_hi - c_lo) + (f_hi - f_lo)) needs float32 only.  This replaced float64 positions
+// with ~2.5x the instructions (the kernel is issue bound, not HBM bound).
 // ---------------------------------------------------------------------------
 #define FB_RSD_IDX_BITS 12
 #define FB_RSD_LPC 8            // lines of sight per CTA (software pipelined)
@@ -105,7 +110,7 @@ template <int N>
 struct RsdGeom {
     static constexpr int NT = N >= 256 ? 256 : (N < 32 ? 32 : N);
     static constexpr int E = (N + NT - 1) / NT;                      // elements per thread
-    static constexpr size_t SMEM = (size_t)N * (8 + 2 * (8 + 4 + 4 + 4));   // zz + 2 x (u, cmax, cmin, y)
+    static constexpr size_t SMEM = (size_t)N * (8 + 2 * (4 + 4 + 4 + 4));   // t0 + 2 x (frac, y, cmax, cmin)
 };
 
 template <int N>
@@ -116,19 +121,19 @@ __global__ void __launch_bounds__(RsdGeom<N>::NT) k_rsd_remap(const float* __res
                                                               float* __restrict__ out, long nlines) {
     constexpr int NT = RsdGeom<N>::NT, E = RsdGeom<N>::E;
     extern __shared__ __align__(16) unsigned char rsd_smem[];
-    double* zz = reinterpret_cast<double*>(rsd_smem);                 // grid [N]
-    double* u2 = zz + N;                                              // wrapped sample positions [2][N]
-    unsigned* cmax2 = reinterpret_cast<unsigned*>(u2 + 2 * N);        // per cell: largest sample (32-bit key)
+    double* t0 = reinterpret_cast<double*>(rsd_smem);                 // (z_l - z_0) / length  [N]
+    float* pf2 = reinterpret_cast<float*>(t0 + N);                    // fraction inside the cell [2][N]
+    float* y2 = pf2 + 2 * N;                                          // sample values [2][N]
+    unsigned* cmax2 = reinterpret_cast<unsigned*>(y2 + 2 * N);        // per cell: largest sample (32-bit key)
     unsigned* cmin2 = cmax2 + 2 * N;                                  // per cell: smallest sample
-    float* y2 = reinterpret_cast<float*>(cmin2 + 2 * N);              // [2][N]
     const int tid = threadIdx.x;
     const double zmin = zgrid[0], zmax = zgrid[N - 1];       // increasing grid (linspace, box.py:79-88)
     const double length = zmax - zmin;
-    const double inv_dz = (double)(N - 1) / length, inv_len = 1.0 / length, inv_H = 1.0 / Hz;
+    const double inv_len = 1.0 / length, c1 = inv_len / Hz;
     // key = position inside the cell (20 bits) | sample index + 1 (12 bits): native 32-bit smem atomics
     constexpr unsigned LOW = (1u << FB_RSD_IDX_BITS) - 1u;
     for (int l = tid; l < N; l += NT) {
-        zz[l] = zgrid[l];
+        t0[l] = (zgrid[l] - zmin) * inv_len;
         cmax2[l] = 0u;
         cmin2[l] = ~0u;
     }
@@ -149,66 +154,62 @@ __global__ void __launch_bounds__(RsdGeom<N>::NT) k_rsd_remap(const float* __res
     __syncthreads();
     int cur = 0;
     for (long ln = line0; ln < line1; ++ln, cur ^= 1) {
-        double* u = u2 + cur * N;
+        float* pf = pf2 + cur * N;
         float* y = y2 + cur * N;
         unsigned *cmax = cmax2 + cur * N, *cmin = cmin2 + cur * N;
         float dnext[E], vnext[E];
         if (ln + 1 < line1) fetch(ln + 1, dnext, vnext);            // in flight while this line is processed
-        // ---- phase 1: wrapped positions, per-cell extremes; reset the other buffer's cells
+        // ---- phase 1: wrapped positions in cell units, per-cell extremes
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int l = tid + e * NT;
             if (l < N) {
-                const double s = zz[l] - (double)vcur[e] * inv_H;     // box.py:422 (float add of v_nl, reciprocal of H)
-                // (s - zmin) % length + zmin with Python's sign convention (box.py:425-426)
-                double r = s - zmin;
-                r -= floor(r * inv_len) * length;
-                if (r < 0.0) r += length;
-                if (r >= length) r -= length;
-                const double w = r + zmin;
-                u[l] = w;
+                // (s - zmin) % length with Python's sign convention (box.py:422-426), as a fraction of the box
+                double t = fma(-(double)vcur[e], c1, t0[l]);
+                t -= floor(t);
+                const double p = t * (double)(N - 1);
+                int c = (int)p;
+                float f = (float)(p - (double)c);
+                if (f >= 1.f) {                                  // rounds onto the next grid point
+                    c += 1;
+                    f = 0.f;
+                }
+                c = min(c, N - 1);
+                pf[l] = f;
                 y[l] = dcur[e];
-                // cell c with zz[c] <= w < zz[c+1] (exact w.r.t. the actual grid values)
-                int c = (int)(r * inv_dz);
-                c = max(0, min(c, N - 1));
-                while (c + 1 < N && w >= zz[c + 1]) ++c;
-                while (c > 0 && w < zz[c]) --c;
-                const float fpos = (float)((w - zz[c]) * inv_dz);          // in [0, 1)
-                const unsigned qpos = min((unsigned)(fmaxf(fpos, 0.f) * 1048576.f), 1048575u);
+                const unsigned qpos = min((unsigned)(f * 1048576.f), 1048575u);
                 const unsigned key = (qpos << FB_RSD_IDX_BITS) | (unsigned)(l + 1);
                 atomicMax(&cmax[c], key);
                 atomicMin(&cmin[c], key);
             }
         }
         __syncthreads();
-        // ---- phase 2: smallest / largest sample, then the bracket of every grid point
-        int cf = 0, cl = N - 1;
-        while (cf < N - 1 && cmin[cf] == ~0u) ++cf;
-        while (cl > 0 && cmax[cl] == 0u) --cl;
-        const double xs_first = u[(int)(cmin[cf] & LOW) - 1], xs_last = u[(int)(cmax[cl] & LOW) - 1];
+        // ---- phase 2: the bracket of every grid point
         const float fill = 0.5f * (y[0] + y[N - 1]);           // box.py:429
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int l = tid + e * NT;
             if (l < N) {
-                const double x = zz[l];
-                float r;
-                if (x < xs_first || x > xs_last) {
-                    r = fill;                                  // outside the sampled range
-                } else {
-                    int il = -1, ih = -1;
-                    for (int c = l - 1; c >= 0; --c)           // largest sample < x
-                        if (cmax[c]) { il = (int)(cmax[c] & LOW) - 1; break; }
-                    for (int c = l; c < N; ++c)                // smallest sample >= x
-                        if (cmin[c] != ~0u) { ih = (int)(cmin[c] & LOW) - 1; break; }
-                    if (ih < 0) ih = il;                       // cannot happen when x <= xs_last
-                    if (il < 0) {
-                        r = y[ih];                             // x == smallest sample
-                    } else {
-                        // differences of nearby float64 positions are exact; the weight only needs float32
-                        const double xl = u[il];
-                        const float wgt = (float)(x - xl) / (float)(u[ih] - xl);
-                        r = fmaf(y[ih] - y[il], wgt, y[il]);
+                int il = -1, ih = -1, clo = 0, chi = 0;
+                for (int c = l - 1; c >= 0; --c) {             // largest sample < z_l
+                    const unsigned k = cmax[c];
+                    if (k) { il = (int)(k & LOW) - 1; clo = c; break; }
+                }
+                for (int c = l; c < N; ++c) {                  // smallest sample >= z_l
+                    const unsigned k = cmin[c];
+                    if (k != ~0u) { ih = (int)(k & LOW) - 1; chi = c; break; }
+                }
+                float r = fill;                                // outside [min s, max s]
+                if (ih >= 0) {
+                    const float fh = pf[ih], yh = y[ih];
+                    if (il >= 0) {
+                        const float fl = pf[il], yl = y[il];
+                        const float num = (float)(l - clo) - fl;
+                        const float den = (float)(chi - clo) + (fh - fl);
+                        const float wgt = den > 0.f ? __fdividef(num, den) : 0.f;
+                        r = fmaf(yh - yl, wgt, yl);
+                    } else if (chi == l && fh == 0.f) {
+                        r = yh;                                // z_l is the smallest sample itself
                     }
                 }
                 out[(size_t)ln * N + l] = r;

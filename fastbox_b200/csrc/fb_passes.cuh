@@ -20,12 +20,6 @@ enum { SRC_NOISE = 0, SRC_PHILOX = 1, SRC_SPEC = 2, SRC_CUBE = 3 };
 #ifndef FB_ROWS_INV_MINB
 #define FB_ROWS_INV_MINB FB_ROWS_MINB
 #endif
-#ifndef FB_ROWS_NOISE_QB
-#define FB_ROWS_NOISE_QB 8
-#endif
-#ifndef FB_ROWS_NOISE_STOCKHAM
-#define FB_ROWS_NOISE_STOCKHAM 0     // noise-cube prologue loads in Stockham order (0: quad order + shared-memory park)
-#endif
 
 template <int N>
 struct RowGeom {
@@ -52,9 +46,20 @@ struct RowsArgs {
     long nrows;                 // na * N
     int flags;
     int kind;
+    int pf_dist;                // rows_inv, noise source: CTA b asks L2 for the rows of CTA b + pf_dist (0 = off)
     KSpace K;
     PkDev pk;
 };
+
+// L2 prefetch of a contiguous block (16-byte aligned, size a multiple of 16): one instruction, no register or
+// shared-memory cost.  The first pass of the inverse transform loads its whole input in the prologue and then
+// computes for a long time, so the loads of one CTA are poorly overlapped by the two other CTAs of the SM; asking
+// L2 for the rows of a CTA that will start ~one wave later turns its HBM latency into an L2 hit.
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// one 128-byte line (strided tiles: every thread asks for one row chunk of the tile a later CTA will load)
+__device__ __forceinline__ void l2_prefetch_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------
 // Row kernels.  Three thread -> mode mappings are used inside one row (see k_rows_inv): quad order
@@ -468,6 +473,30 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
 
     const int rl = threadIdx.x / T, t = threadIdx.x % T;
     const long row_raw = (long)blockIdx.x * G::RB + rl;
+    if constexpr (SRC == SRC_NOISE && G::RB * N * sizeof(float) % 16 == 0 && G::RB <= N) {
+        // rows of the CTA pf_dist blocks ahead: RB consecutive rows (a, b0 .. b0+RB-1) of re / im and their mirror
+        // rows (N-a, N-b), a contiguous block as well (b0 = 0: row 0 and rows N-RB+1 .. N-1)
+        const long prow = ((long)blockIdx.x + A.pf_dist) * G::RB;
+        if (A.pf_dist > 0 && threadIdx.x < 4 && prow < A.nrows) {
+            const int pa = A.K.a0 + (int)(prow / N), pb = (int)(prow % N);
+            const int pam = (N - pa) & (N - 1);
+            const float* base = (threadIdx.x & 1) ? A.im : A.re;
+            constexpr unsigned ROWB = N * sizeof(float);
+            if (threadIdx.x < 2) {
+                l2_prefetch(base + ((size_t)pa * N + pb) * N, G::RB * ROWB);
+            } else if (pb > 0) {
+                l2_prefetch(base + ((size_t)pam * N + (N - pb - G::RB + 1)) * N, G::RB * ROWB);
+            } else {
+                l2_prefetch(base + (size_t)pam * N * N, ROWB);
+                if (G::RB > 1) l2_prefetch(base + ((size_t)pam * N + (N - G::RB + 1)) * N, (G::RB - 1) * ROWB);
+            }
+        }
+    }
+    if constexpr (SRC == SRC_SPEC && (G::RB * N * sizeof(float2)) % 16 == 0) {
+        const long prow = ((long)blockIdx.x + A.pf_dist) * G::RB;       // stored spectrum: RB contiguous rows
+        if (A.pf_dist > 0 && threadIdx.x == 0 && prow + G::RB <= A.nrows)
+            l2_prefetch(A.src + (size_t)prow * N, G::RB * N * sizeof(float2));
+    }
     const bool rvalid = row_raw < A.nrows;
     const long row_id = rvalid ? row_raw : A.nrows - 1;
     const int al = (int)(row_id / N);
@@ -498,58 +527,8 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_INV_MINB) k_rows_
     if (fast && (A.flags & FB_F_FILTER)) fast_base *= __ldg(&A.K.tperp[a * N + b]);
 
     bool fast_done = false;
-#if FB_ROWS_NOISE_STOCKHAM
-    if constexpr (T > 1 && SRC == SRC_NOISE) {
-        if (fast) {
-            // Noise cubes, common configuration: every thread loads ITS Stockham-order modes c = t + T*q straight
-            // from HBM (a warp still touches 128 consecutive bytes per request, so the wavefront count of the
-            // loads equals that of 16-byte quad loads) and parks the combined spectrum at its natural position:
-            // consecutive lanes write consecutive modes.  The quad-order version parked with 32-byte lane
-            // strides (4x the wavefronts of a dense store); the L1 data pipe is what limits this kernel.
-            fast_done = true;
-            const bool has_f = (A.flags & FB_F_FILTER) != 0, has_s = (A.flags & FB_F_SQRTPK) != 0;
-            const int mt = (N - t) & (N - 1);                             // mirror cell of mode t
-            const float* re_g = A.re + row_g + t;
-            const float* im_g = A.im + row_g + t;
-            const float* re_m = A.re + row_m + mt + (t == 0 ? N : 0);     // mirror of t + T*q: mt - T*q (q >= 1)
-            const float* im_m = A.im + row_m + mt + (t == 0 ? N : 0);
-            constexpr int QB = FB_ROWS_NOISE_QB;                          // modes per batch of loads (register budget)
-            const bool do_store = A.spec_out != nullptr && rvalid;
-            float2* park = sm + sl(t);
-#pragma unroll
-            for (int q0 = 0; q0 < P; q0 += QB) {
-                float gr[QB], gi[QB], mr[QB], mi[QB];
-#pragma unroll
-                for (int i = 0; i < QB; ++i) {
-                    const int q = q0 + i;
-                    gr[i] = __ldg(re_g + T * q);
-                    gi[i] = __ldg(im_g + T * q);
-                    mr[i] = q == 0 ? __ldg(A.re + row_m + mt) : __ldg(re_m - T * q);
-                    mi[i] = q == 0 ? __ldg(A.im + row_m + mt) : __ldg(im_m - T * q);
-                }
-#pragma unroll
-                for (int i = 0; i < QB; ++i) {
-                    const int q = q0 + i;
-                    const int c = t + T * q;
-                    float f = fast_base;
-                    if (has_f) f *= __ldg(A.K.tpar + c);
-                    if (has_s) {
-                        const int mc = q < P / 2 ? c : c - N;             // |m_c| (c = N/2 either way)
-                        float am = sqrtp_bittable_nz(A.K, sab_f + (float)(mc * mc) * A.K.inv_lz2);
-                        if (q == 0 && dc_row && t == 0) am = 0.f;         // nan_to_num(P(0)) = 0, box.py:167
-                        f *= am;
-                    }
-                    const float2 h = make_float2((gr[i] + mr[i]) * f, (gi[i] - mi[i]) * f);
-                    if (do_store) A.spec_out[row_local + c] = h;
-                    if constexpr (T % 16 == 0) park[q * RowLayout<N>::pstride(T)] = h;     // natural order, dense per warp
-                    else sm[sl(c)] = h;
-                }
-            }
-        }
-    }
-#endif
     if constexpr (T > 1 && (SRC == SRC_NOISE || SRC == SRC_PHILOX)) {
-        if (fast && !fast_done) {
+        if (fast) {
             // Common configuration (bit-table sqrt(P) or none, separable filter or none, plain
             // field).  The loop body is free of branches (options are predicated loads / selects),
             // so the loads of later quads are scheduled above the arithmetic of earlier ones.
@@ -755,6 +734,13 @@ __global__ void __launch_bounds__(RowGeom<N>::THREADS, FB_ROWS_MINB) k_rows_fwd(
     const bool do_pk = (A.flags & FB_F_PK) != 0;
     const bool poles = (A.flags & FB_F_POLES) != 0;
     const size_t row_local = ((size_t)al * N + b) * N;
+    if constexpr ((G::RB * N * sizeof(float2)) % 16 == 0) {
+        const long prow = ((long)blockIdx.x + A.pf_dist) * G::RB;       // RB contiguous rows of the block pf_dist ahead
+        if (A.pf_dist > 0 && threadIdx.x == 0 && prow + G::RB <= A.nrows) {
+            l2_prefetch(A.work + (size_t)prow * N, G::RB * N * sizeof(float2));
+            if (A.cross) l2_prefetch(A.cross + (size_t)prow * N, G::RB * N * sizeof(float2));
+        }
+    }
     float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) v[q] = A.work[row_local + t + T * q];
@@ -830,7 +816,7 @@ template <int N, int CZ, int S, bool SLAB>
 __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const float2* __restrict__ in,
                                                                      float2* __restrict__ out, const SlabView vin,
                                                                      const SlabView vout,
-                                                                     const float2* __restrict__ tw) {
+                                                                     const float2* __restrict__ tw, int pf_dist) {
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -838,6 +824,15 @@ __global__ void __launch_bounds__(ColGeom<N, CZ>::THREADS) k_cols_c2c(const floa
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
     const int plane = blockIdx.y;
     const size_t zc = (size_t)blockIdx.x * CZ + col;
+    if constexpr (!SLAB) {
+        if (pf_dist > 0) {                             // the tile of the CTA pf_dist blocks ahead -> L2
+            const unsigned id = blockIdx.y * gridDim.x + blockIdx.x + pf_dist;
+            const unsigned pp = id / gridDim.x, pz = id - pp * gridDim.x;
+            if (pp < gridDim.y)
+                for (int r = threadIdx.x; r < N; r += ColGeom<N, CZ>::THREADS)
+                    l2_prefetch_line(in + ((size_t)pp * N + r) * N + (size_t)pz * CZ);
+        }
+    }
     float2 v[P];
     if constexpr (SLAB) {
 #pragma unroll

@@ -102,81 +102,12 @@ __global__ void __launch_bounds__(256) k_pca_cov(const double* __restrict__ x, c
         }
 }
 
-// Tensor-core variant: the same 64 x 64 tile and pixel slices, the inner product by FP64 MMA
-// (mma.sync m8n8k4, f64 in / f64 accumulate: identical precision class, different summation order).
-// 8 warps = 2 (f) x 4 (g); a warp owns 32 x 16 outputs = 4 x 2 MMA tiles.  Fragment layouts (PTX ISA):
-// A (8x4, row) lane l holds A[l/4][l%4]; B (4x8, col) lane l holds B[l%4][l/4]; C (8x8) lane l holds
-// C[l/4][2(l%4)], C[l/4][2(l%4)+1].  Per 4 pixels a lane issues 6 shared loads for 8 MMAs (64 FMA/lane);
-// the SIMT kernel needs 32 loads for the same work.  Measured at 1024^3: 99 ms against 88 ms for the SIMT kernel
-// (both ~12-13 TFLOP/s of the 34 / 37 TFLOP/s that fb_bench_fp64 measures for FMA / MMA chains), so the limit
-// is not the FP64 pipe; kept as an opt-in (FB_PCA_MMA=1) and covered by the parity tests.
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+// (An FP64 tensor-core variant of this kernel -- mma.sync m8n8k4 on the same tiles -- was measured at 99 ms against
+// 88 ms for the SIMT kernel at 1024^3 and removed: the limit is not the FP64 pipe, see profiles/README.md.)
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {      // fb_bench_fp64 probe
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
-}
-
-__global__ void __launch_bounds__(256) k_pca_cov_mma(const double* __restrict__ x, const double* __restrict__ mean,
-                                                      int nf, size_t npix, int ntile, double* __restrict__ cov) {
-    // row stride 72 doubles = 576 B = 64 (mod 128): the 4 pixel rows of a fragment fall on two bank halves
-    __shared__ double sa[PCA_KT][PCA_TILE + 8], sb[PCA_KT][PCA_TILE + 8];
-    int ti = 0, rem = blockIdx.x;
-    while (rem >= ntile - ti) {
-        rem -= ntile - ti;
-        ++ti;
-    }
-    const int tj = ti + rem;
-    const int f0 = ti * PCA_TILE, g0 = tj * PCA_TILE;
-    const size_t per_slice = (npix + gridDim.y - 1) / gridDim.y;
-    const size_t p0 = (size_t)blockIdx.y * per_slice;
-    const size_t p1 = p0 + per_slice < npix ? p0 + per_slice : npix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wf = (warp >> 2) * 32, wg = (warp & 3) * 16;                // warp tile origin inside the CTA tile
-    const int lk = lane & 3, lm = lane >> 2;                              // fragment coordinates
-    const int lc = threadIdx.x % PCA_TILE, lr = threadIdx.x / PCA_TILE;   // loader: 64 channels x 4 pixel rows
-    double acc[4][2][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const double ma = (f0 + lc) < nf ? __ldg(&mean[f0 + lc]) : 0.0;
-    const double mb = (g0 + lc) < nf ? __ldg(&mean[g0 + lc]) : 0.0;
-    for (size_t pb = p0; pb < p1; pb += PCA_KT) {
-#pragma unroll
-        for (int k = lr; k < PCA_KT; k += 4) {
-            const size_t p = pb + k;
-            double va = 0.0, vb = 0.0;
-            if (p < p1) {
-                if (f0 + lc < nf) va = __ldg(&x[p * nf + f0 + lc]) - ma;
-                if (g0 + lc < nf) vb = __ldg(&x[p * nf + g0 + lc]) - mb;
-            }
-            sa[k][lc] = va;
-            sb[k][lc] = vb;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k0 = 0; k0 < PCA_KT; k0 += 4) {
-            double a[4], b[2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = sa[k0 + lk][wf + 8 * i + lm];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) b[j] = sb[k0 + lk][wg + 8 * j + lm];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int f = f0 + wf + 8 * i + lm, g = g0 + wg + 8 * j + 2 * lk + c;
-                if (f < nf && g < nf) atomicAdd(&cov[(size_t)f * nf + g], acc[i][j][c]);
-            }
 }
 
 // mirror the upper-triangle tiles into the lower triangle and apply the 1/(npix-1) of np.cov
@@ -353,10 +284,7 @@ int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* 
     const size_t max_slices = (npix + PCA_KT - 1) / PCA_KT;
     if ((size_t)slices > max_slices) slices = (int)max_slices;
     if (slices < 1) slices = 1;
-    if (env_int("FB_PCA_MMA", 0))                        // measured no faster (99 vs 88 ms at 1024^3): opt-in
-        k_pca_cov_mma<<<dim3(ntri, slices), 256, 0, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
-    else
-        k_pca_cov<<<dim3(ntri, slices), 256, 0, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
+    k_pca_cov<<<dim3(ntri, slices), 256, 0, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
     FB_LAUNCH_CHECK();
     k_pca_cov_finish<<<dim3((nf + 255) / 256, nf), 256, 0, p->stream>>>(d_cov, nf, 1.0 / (double)(npix - 1));
     FB_LAUNCH_CHECK();

@@ -10,7 +10,9 @@ static int launch_n(fb_plan* p, const RowsArgs& a) {
     auto kern = k_rows_fwd<N, DOFFT>;
     if (set_smem(kern, G::SMEM)) return -2;
     const long blocks = (a.nrows + G::RB - 1) / G::RB;
-    kern<<<(unsigned)blocks, G::THREADS, G::SMEM, p->stream>>>(a);
+    RowsArgs b = a;
+    b.pf_dist = env_int("FB_ROWS_PF", FB_ROWS_PF_DEFAULT);     // L2 prefetch distance in CTAs
+    kern<<<(unsigned)blocks, G::THREADS, G::SMEM, p->stream>>>(b);
     FB_LAUNCH_CHECK();
     return 0;
 }

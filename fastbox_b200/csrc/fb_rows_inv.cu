@@ -6,6 +6,7 @@
 #error "compile with -DFB_SRC=0..3"
 #endif
 
+
 namespace fb {
 
 #if FB_SRC == 0
@@ -24,7 +25,9 @@ static int launch_n(fb_plan* p, const RowsArgs& a) {
     auto kern = k_rows_inv<N, FB_SRC>;
     if (set_smem(kern, G::SMEM_INV)) return -2;
     const long blocks = (a.nrows + G::RB - 1) / G::RB;
-    kern<<<(unsigned)blocks, G::THREADS, G::SMEM_INV, p->stream>>>(a);
+    RowsArgs b = a;
+    b.pf_dist = env_int("FB_ROWS_PF", FB_ROWS_PF_DEFAULT);     // L2 prefetch distance in CTAs (noise and stored-spectrum sources)
+    kern<<<(unsigned)blocks, G::THREADS, G::SMEM_INV, p->stream>>>(b);
     FB_LAUNCH_CHECK();
     return 0;
 }

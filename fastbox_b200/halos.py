@@ -90,6 +90,3 @@ class HaloDistribution(object):
         plan.halo_catalogue(cnt, u, cat, nh)
         return cat
 
-
-def box_len(L, N):
-    return L / N

@@ -131,9 +131,8 @@ def test_pca_filter_matches_reference_golden(gpu):
         fb.filters.pca_filter(g["pca_cube"], nmodes=0)
 
 
-@pytest.mark.parametrize("N,mma", [(8, 0), (64, 0), (128, 0), (64, 1), (256, 1)])
-def test_pca_covariance_and_projection_vs_numpy(gpu, monkeypatch, N, mma):
-    monkeypatch.setenv("FB_PCA_MMA", str(mma))            # 1: FP64 tensor-core variant of the covariance kernel
+@pytest.mark.parametrize("N", [8, 64, 128, 256])
+def test_pca_covariance_and_projection_vs_numpy(gpu, N):
     rng = np.random.default_rng(N)
     nu = np.linspace(1.0, 2.0, N)
     cube = (50.0 * rng.uniform(0.5, 1.5, (N, N, 1)) * nu[None, None, :] ** -2.7

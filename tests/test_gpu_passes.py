@@ -111,41 +111,3 @@ def test_y_pass_tma_pipelined(gpu, monkeypatch, N, cz, sign):
     assert rel_l2(out["1"], ref) < TOL
     assert np.array_equal(out["1"], out["0"])
     plan.close()
-
-
-@pytest.mark.parametrize("N", [512, 1024])
-def test_x_passes_tma_pipelined(gpu, monkeypatch, N):
-    """
-    Persistent TMA-pipelined x passes (fb_x_tma.cu) == numpy.fft and == the per-thread kernels bit for bit, incl.
-    the exp / sum epilogue.  ncols gives every CTA several tiles (both buffers reused, ragged last round).
-    """
-    cz = 32 if N == 512 else 16
-    ncols = cz * (148 * 3 + 17)
-    rng = np.random.default_rng(N)
-    f = (0.3 * rng.standard_normal((N, ncols))).astype(np.float32)
-    plan = _lib.Plan(N, 100., 100., 100.)
-    dfield = plan.upload(f)
-    spec, back, sums = {}, {}, {}
-    for tma in ("1", "0"):
-        monkeypatch.setenv("FB_X_TMA", tma)
-        dspec = plan.alloc((N // 2 + 1) * ncols * 8)
-        plan.fft_pass_x_r2c(dfield, dspec, ncols)
-        plan.sync()
-        spec[tma] = plan.download(dspec, (N // 2 + 1, ncols), np.complex64)
-        dback = plan.alloc(N * ncols * 4)
-        sums[tma] = plan.fft_pass_x_c2r(dspec, dback, ncols, scale=1.0 / N)
-        back[tma] = plan.download(dback, (N, ncols), np.float32)
-        sums[tma + "e"] = plan.fft_pass_x_c2r(dspec, dback, ncols, flags=_lib.F_EXP, scale=1.0 / N)
-        back[tma + "e"] = plan.download(dback, (N, ncols), np.float32)
-        dspec.free()
-        dback.free()
-    assert rel_l2(spec["1"], np.fft.rfft(f.astype(np.float64), axis=0)) < TOL
-    assert rel_l2(back["1"], f.astype(np.float64)) < TOL
-    assert rel_l2(back["1e"], np.exp(f.astype(np.float64))) < TOL
-    assert np.array_equal(spec["1"], spec["0"])
-    assert np.array_equal(back["1"], back["0"])
-    assert np.array_equal(back["1e"], back["0e"])
-    for k in ("", "e"):
-        assert abs(sums["1" + k][0] - sums["0" + k][0]) <= 1e-6 * abs(sums["0" + k][0]) + 1e-3
-        assert abs(sums["1" + k][1] - sums["0" + k][1]) <= 1e-6 * abs(sums["0" + k][1])
-    plan.close()
