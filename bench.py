@@ -552,7 +552,7 @@ def run_multi(args, rank, world, local_rank):
     os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     mode = os.environ.get("FB_DIST_MODE", "p2p")           # p2p: exchange inside the library; nccl: all_to_all_single
-    chunks = int(os.environ.get("FB_CHUNKS", "4"))
+    chunks = int(os.environ.get("FB_CHUNKS", "8"))
     while chunks > 1 and ((N // 2) // world) % chunks:
         chunks //= 2
     flags = _lib.F_SQRTPK | _lib.F_FILTER
@@ -619,9 +619,21 @@ def run_multi(args, rank, world, local_rank):
 
     # the exchange alone, for the NVLink roofline
     a2a = max(fbd.alltoall_bytes_per_rank(N, world))
+    push_sweep = None
     if mode == "p2p":
         dist.barrier()
         t_x_alone = plan.dist_bench_exchange(3) * 1e-3
+        if os.environ.get("FB_PUSH_SWEEP") and int(os.environ.get("FB_DIST_XMODE", "2")) == 2:
+            # tuning: the copy kernel alone for several CTA counts per peer (collective: same order on all ranks)
+            push_sweep = {}
+            keep = int(os.environ.get("FB_DIST_PUSH_CTAS", "0"))
+            for c in (2, 3, 4, 6, 8, 12, 16, 24):
+                plan.dist_set_option("push_ctas", c)
+                dist.barrier()
+                tt = torch.tensor([plan.dist_bench_exchange(3)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                push_sweep[str(c)] = {"ms": float(tt[0]), "GBs": a2a / (float(tt[0]) * 1e-3) / 1e9}
+            plan.dist_set_option("push_ctas", keep if keep > 0 else max(4, 48 // max(1, world - 1)))
     else:
         xs = []
         for _ in range(3):
@@ -660,11 +672,16 @@ def run_multi(args, rank, world, local_rank):
         nv = a2a / t_x_alone / 1e9
         check = dict(check or {}, count_sum=int(pk["count"].sum()), count_sum_expected=N ** 3,
                      count_sum_ok=bool(int(pk["count"].sum()) == N ** 3), parseval_ratio=parseval)
-        how = ("exchange inside the library: the y pass stores straight into the peers' receive buffers over "
-               "NVLink (CUDA IPC), %d first-pass chunks overlap the stores, device-side epoch flags, no NCCL on "
-               "the data path" % chunks) if mode == "p2p" else \
+        xmode = int(os.environ.get("FB_DIST_XMODE", "2"))
+        mech = {0: "the y pass stores straight into the peers' receive buffers",
+                1: "the y pass writes per-destination blocks that the copy engines push into the peers' receive buffers",
+                2: "the y pass writes per-destination blocks that a high-priority copy kernel (a few CTAs per peer, "
+                   "16-byte peer stores) pushes into the peers' receive buffers while the k-space passes of the next "
+                   "chunk run"}[xmode]
+        how = ("exchange inside the library over NVLink peer memory (CUDA IPC): %s; %d chunks of planes, device-side "
+               "epoch flags, no NCCL on the data path" % (mech, chunks)) if mode == "p2p" else \
               ("one NCCL all_to_all_single in %d chunks overlapped with the k-space passes" % chunks)
-        nvlink = {"bytes_sent_per_gpu": a2a, "exchange_alone_ms": t_x_alone * 1e3, "achieved_GBs": nv,
+        nvlink = {"bytes_sent_per_gpu": a2a, "exchange_alone_ms": t_x_alone * 1e3, "achieved_GBs": nv, "push_sweep": push_sweep,
                   "frac_of_900": nv / 900.0, "frac_of_measured_770": nv / 770.0, "mode": mode}
         if mode == "p2p":
             nvlink.update({"in_pipeline": {"kspace_passes_with_peer_stores_ms": pass_ms[0], "wait_for_peers_ms": pass_ms[1],

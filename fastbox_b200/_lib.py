@@ -87,6 +87,7 @@ SIGNATURES = {
     "fb_dist_barrier": (_i, [_vp]),
     "fb_dist_realise": (_i, [_vp, _u64, _i, _f, _i, _i, _vp, C.POINTER(PkResult), C.POINTER(_d)]),
     "fb_dist_bench_exchange": (_i, [_vp, _i, C.POINTER(_f)]),
+    "fb_dist_set_option": (_i, [_vp, C.c_char_p, _i]),
     "fb_dist_power_spectrum": (_i, [_vp, _vp, _i, _i, C.POINTER(PkResult)]),
     "fb_bench_strided_copy": (_i, [_vp, _sz, _i, _i, C.POINTER(_d)]),
     "fb_last_timings": (_i, [_vp, C.POINTER(_f), _i]),
@@ -453,6 +454,9 @@ class Plan(object):
                                        _ptr(field_out), C.byref(st) if st is not None else None,
                                        sums if want_sums else None))
         return res, (sums[0], sums[1])
+
+    def dist_set_option(self, key, value):
+        check(self.lib.fb_dist_set_option(self.h, key.encode(), int(value)))
 
     def dist_bench_exchange(self, iters=3):
         ms = C.c_float()

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(BeamGeom<N>::CT* FftCfg<N>::T) k_beam_y_r2c(co
 template <int N, bool SETUP>
 __global__ void __launch_bounds__(BeamGeom<N>::CZB* FftCfg<2 * N>::T, (BeamGeom<N>::CZB * FftCfg<2 * N>::T <= 512) ? 2 : 1)
     k_beam_x(float2* __restrict__ Y, float2* __restrict__ BS, const float* __restrict__ inv,
-             const float2* __restrict__ tw) {
+             const float2* __restrict__ tw, int pf_dist) {
     constexpr int NF = 2 * N;
     using C = FftCfg<NF>;
     using G = BeamGeom<N>;
@@ -113,6 +113,23 @@ __global__ void __launch_bounds__(BeamGeom<N>::CZB* FftCfg<2 * N>::T, (BeamGeom<
     const int zt = blockIdx.x / (CT / CZ), c = (blockIdx.x % (CT / CZ)) * CZ + col;
     float2* y = Y + beam_tile(N, G::NZT, CT, ky, zt, N) + c;
     float2* bs = BS + beam_tile(N, G::NZT, CT, ky, zt, NF) + c;
+    if constexpr (!SETUP && N >= 256) {
+        // L2 prefetch of the (contiguous) Y and BS tiles of the CTA pf_dist blocks ahead, once per tile, in 32 KB pieces
+        constexpr int PER = CT / CZ;                                 // CTAs per tile
+        constexpr unsigned PIECE = (size_t)N * CT * sizeof(float2) >= 32768 ? 32768u : (unsigned)((size_t)N * CT * sizeof(float2));
+        constexpr int NY = (int)((size_t)N * CT * sizeof(float2) / PIECE), NB = 2 * NY;
+        if (pf_dist > 0 && (int)threadIdx.x < NY + NB) {
+            const unsigned id = blockIdx.y * gridDim.x + blockIdx.x + pf_dist;
+            const unsigned pk = id / gridDim.x, pbx = id - pk * gridDim.x;
+            if (pk <= (unsigned)N && pbx % PER == 0) {
+                const int pzt = pbx / PER;
+                const unsigned char* base = threadIdx.x < NY
+                    ? reinterpret_cast<const unsigned char*>(Y + beam_tile(N, G::NZT, CT, pk, pzt, N)) + threadIdx.x * PIECE
+                    : reinterpret_cast<const unsigned char*>(BS + beam_tile(N, G::NZT, CT, pk, pzt, NF)) + (threadIdx.x - NY) * PIECE;
+                l2_prefetch(base, PIECE);
+            }
+        }
+    }
     float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) {
@@ -204,7 +221,8 @@ static int beam_pass_b(fb_plan* p, float2* Y, float2* BS, const float* inv) {
     auto kern = k_beam_x<N, SETUP>;
     const size_t smem = (size_t)(2 * N + 2 * N / 16) * G::CZB * sizeof(float2);
     if (set_smem(kern, smem)) return -2;
-    kern<<<dim3(G::NZT * (G::CT / G::CZB), N + 1), G::CZB * FftCfg<2 * N>::T, smem, p->stream>>>(Y, BS, inv, p->tw);
+    kern<<<dim3(G::NZT * (G::CT / G::CZB), N + 1), G::CZB * FftCfg<2 * N>::T, smem, p->stream>>>(
+        Y, BS, inv, p->tw, env_int("FB_BEAM_PF", FB_BEAM_PF_DEFAULT));
     FB_LAUNCH_CHECK();
     return 0;
 }

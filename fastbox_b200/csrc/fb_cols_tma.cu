@@ -160,6 +160,8 @@ static int launch_t(fb_plan* p, const float2* in, float2* out, int nplanes, int 
     return 0;
 }
 
+bool tma_available() { return encode_fn() != nullptr; }
+
 bool cols_tma_available(int N, int cz) {
     if (!encode_fn()) return false;
     if (N == 512) return cz == 8 || cz == 16;

@@ -19,7 +19,7 @@
 
 #define FB_DIST_MAX_CHUNKS 16
 #ifndef FB_DIST_XMODE_DEFAULT
-#define FB_DIST_XMODE_DEFAULT 0
+#define FB_DIST_XMODE_DEFAULT 2
 #endif
 #define FB_DIST_HANDLE_BYTES 128
 
@@ -552,6 +552,24 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
     return 0;
 }
 
+int fb_dist_set_option(fb_plan* p, const char* key, int value) {
+    fb_dist_state* d = p->dist;
+    FB_CHECK(d && key, "fb_dist_set_option: call fb_dist_init first");
+    if (!strcmp(key, "push_ctas")) {
+        FB_CHECK(value >= 1 && value <= 64, "push_ctas must be in 1..64");
+        d->push_ctas = value;
+    } else if (!strcmp(key, "xmode")) {
+        FB_CHECK(value >= 0 && value <= 2, "xmode must be 0, 1 or 2");
+        d->xmode = value;
+    } else if (!strcmp(key, "cz_cols")) {
+        d->cz_cols = value;
+    } else {
+        set_error("fb_dist_set_option: unknown key '%s'", key);
+        return -1;
+    }
+    return 0;
+}
+
 // The exchange alone, for the NVLink roofline: y pass over the local planes (whatever `work` holds) storing into
 // the peers' receive buffers, then the barrier; average milliseconds per iteration (CUDA events on the plan stream).
 int fb_dist_bench_exchange(fb_plan* p, int iters, float* ms_out) {
@@ -567,10 +585,32 @@ int fb_dist_bench_exchange(fb_plan* p, int iters, float* ms_out) {
     while ((1 << vout.ny_shift) < ny) ++vout.ny_shift;
     for (int r = 0; r < d->world; ++r)
         vout.base[r] = reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) + (size_t)p->a0 * ny * N;
+    // xmode 2: the copy kernel alone over the whole per-destination staging array (what the pipeline pushes per step)
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    if (d->xmode == 2) {
+        FB_CHECK(d->send != nullptr, "fb_dist_bench_exchange: run fb_dist_realise once first (staging array)");
+        // blocks as laid out by a one-chunk step: [dest][plane][y'][z], na planes each
+        const size_t blk = (size_t)na * ny * N;
+        pa.n16 = blk * sizeof(float2) / sizeof(uint4);
+        for (int k = 0; k < d->world - 1; ++k) {
+            const int r = (d->rank + 1 + k) % d->world;
+            pa.src[k] = reinterpret_cast<const uint4*>(d->send + (size_t)r * blk);
+            pa.dst[k] = reinterpret_cast<uint4*>(reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) +
+                                                 (size_t)p->a0 * ny * N);
+        }
+    }
     float total = 0.f;
     for (int it = 0; it < iters + 1; ++it) {                 // first iteration = warm-up, aligns the ranks
         FB_CUDA(cudaEventRecord(p->ev[4], p->stream));
-        if (launch_cols_views(p, plain_view(p->work), vout, na, +1, p->stream, d->cz_cols)) return -3;
+        if (d->xmode == 2) {
+            if (d->world > 1) {
+                k_dist_push<<<dim3(d->push_ctas, d->world - 1), 512, 0, p->stream>>>(pa);
+                FB_LAUNCH_CHECK();
+            }
+        } else if (launch_cols_views(p, plain_view(p->work), vout, na, +1, p->stream, d->cz_cols)) {
+            return -3;
+        }
         if (dist_signal(p)) return -3;
         if (dist_wait(p)) return -3;
         FB_CUDA(cudaEventRecord(p->ev[5], p->stream));

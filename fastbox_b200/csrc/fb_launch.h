@@ -17,6 +17,7 @@ SlabView block_view(float2* base, int ny, int nplanes, int N);
 int launch_cols_views(fb_plan* p, const SlabView& vin, const SlabView& vout, int nplanes, int sign, cudaStream_t st,
                       int cz_hint);
 bool cols_tma_available(int N, int cz);
+bool tma_available();          // the driver exposes cuTensorMapEncodeTiled
 int launch_cols_tma(fb_plan* p, const float2* in, float2* out, int nplanes, int sign, int cz, cudaStream_t st);
 #ifndef FB_COLS_TMA_DEFAULT
 #define FB_COLS_TMA_DEFAULT 1
@@ -27,6 +28,12 @@ int launch_cols_tma(fb_plan* p, const float2* in, float2* out, int nplanes, int 
 // passes (one line per thread, rows a whole plane apart) cost 0.6 ms and was removed.
 #ifndef FB_ROWS_PF_DEFAULT
 #define FB_ROWS_PF_DEFAULT 74
+#endif
+#ifndef FB_X_PF_DEFAULT
+#define FB_X_PF_DEFAULT 0          // x passes: tile prefetch through the bulk-tensor engine (one thread per CTA)
+#endif
+#ifndef FB_BEAM_PF_DEFAULT
+#define FB_BEAM_PF_DEFAULT 0       // beam x pass: contiguous Y / BS tiles of the CTA that many blocks ahead
 #endif
 #ifndef FB_COLS_PF_DEFAULT
 #define FB_COLS_PF_DEFAULT 74

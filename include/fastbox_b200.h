@@ -270,6 +270,9 @@ int fb_dist_realise(fb_plan* plan, uint64_t seed, int flags, float scale, int ch
                     fb_pk_result* pk, double* sums_out);
 /* the exchange alone (y pass storing into the peers + barrier), average ms per iteration: NVLink roofline */
 int fb_dist_bench_exchange(fb_plan* plan, int iters, float* ms_out);
+/* tuning knobs of the exchange: "xmode" (0 peer stores of the y pass, 1 copy engines, 2 copy kernel), "push_ctas"
+ * (CTAs per peer of the copy kernel), "cz_cols" (columns per tile of the exchanging y pass)                     */
+int fb_dist_set_option(fb_plan* plan, const char* key, int value);
 /* binned P(k) of the sharded real field (box.py:736-764); field: DEVICE float32 [N][ny][N].
  * phase 0 = all; 1 = x pass + signal; 2 = wait + k-space passes + signal; 3 = wait + sum.               */
 int fb_dist_power_spectrum(fb_plan* plan, const float* field, int flags, int phase, fb_pk_result* pk);
