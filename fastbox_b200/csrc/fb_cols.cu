@@ -105,28 +105,14 @@ static int launch_x_t(fb_plan* p, const XArgs& a, bool inverse) {
         return -1;
     }
     const unsigned grid = (unsigned)(a.ncols / CZ);
-    XArgs b = a;
-    b.pf_dist = 0;
-    const int pf = env_int("FB_X_PF", FB_X_PF_DEFAULT);
-    if (N >= 512 && pf > 0 && !a.plane_off && tma_available()) {
-        // tensor maps of the tiles: spectrum rows of 2*CZ floats (c2r input) or field rows of CZ floats (r2c input)
-        constexpr int M = N / 2;
-        bool ok;
-        if (inverse)
-            ok = make_tensor_map_2d(&b.pf_main, a.spec, 2ull * a.ncols, M + 1, a.ncols * sizeof(float2), 2 * CZ, 256) == 0 &&
-                 make_tensor_map_2d(&b.pf_nyq, a.spec, 2ull * a.ncols, M + 1, a.ncols * sizeof(float2), 2 * CZ, 1) == 0;
-        else
-            ok = make_tensor_map_2d(&b.pf_main, a.field_in, a.ncols, N, a.ncols * sizeof(float), CZ, 256) == 0;
-        if (ok) b.pf_dist = pf;
-    }
     if (inverse) {
         auto kern = k_x_c2r<N, CZ>;
         if (set_smem(kern, G::SMEM)) return -2;
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(b);
+        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(a);
     } else {
         auto kern = k_x_r2c<N, CZ>;
         if (set_smem(kern, G::SMEM)) return -2;
-        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(b);
+        kern<<<grid, G::THREADS, G::SMEM, p->stream>>>(a);
     }
     FB_LAUNCH_CHECK();
     return 0;

@@ -25,15 +25,13 @@ int launch_cols_tma(fb_plan* p, const float2* in, float2* out, int nplanes, int 
 // L2 prefetch distance in CTAs (0 = off): a CTA asks L2 for the input of the CTA that many blocks ahead.
 // Measured at 1024^3 (profiles/README.md): first pass 3.06 -> 2.79 ms for any distance in 37..185 (worse beyond
 // 300: the lines are evicted before use), per-thread y pass 1.68 -> 1.54 ms at 74; the same trick on the x
-// passes (one line per thread, rows a whole plane apart) cost 0.6 ms and was removed.
+// passes (rows a whole plane apart: per-thread line prefetches as well as one bulk-tensor prefetch per CTA)
+// cost 0.5-0.6 ms at every distance and was removed.
 #ifndef FB_ROWS_PF_DEFAULT
 #define FB_ROWS_PF_DEFAULT 74
 #endif
-#ifndef FB_X_PF_DEFAULT
-#define FB_X_PF_DEFAULT 0          // x passes: tile prefetch through the bulk-tensor engine (one thread per CTA)
-#endif
 #ifndef FB_BEAM_PF_DEFAULT
-#define FB_BEAM_PF_DEFAULT 0       // beam x pass: contiguous Y / BS tiles of the CTA that many blocks ahead
+#define FB_BEAM_PF_DEFAULT 32      // beam x pass: contiguous Y / BS tiles of the CTA that many blocks ahead (17.2 -> 16.5 ms)
 #endif
 #ifndef FB_COLS_PF_DEFAULT
 #define FB_COLS_PF_DEFAULT 74

@@ -8,7 +8,6 @@
 // Forward (P(k)) order is the mirror image: xr2c, cols, rows (+ histogram epilogue).
 #pragma once
 #include "fb_kspace.cuh"
-#include "fb_tma.cuh"
 
 namespace fb {
 
@@ -880,17 +879,7 @@ struct XArgs {
     // NVLink); nranks = 0: everything goes to spec_out
     float2* peer_out[FB_MAX_RANKS];
     int nranks, per_shift;
-    // L2 prefetch of the tile pf_dist CTAs ahead by ONE thread through the bulk-tensor engine (tile rows are a whole
-    // plane apart: per-thread line prefetches cost more LSU slots than they saved).  pf_main: boxes of 256 rows,
-    // pf_nyq: the single Nyquist row of the spectrum tile (c2r only).
-    alignas(64) CUtensorMap pf_main;
-    alignas(64) CUtensorMap pf_nyq;
-    int pf_dist;
 };
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
-                 : "memory");
-}
 
 template <int N, int CZ>
 struct XGeom {
@@ -902,7 +891,7 @@ struct XGeom {
 };
 
 template <int N, int CZ>
-__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x_c2r(const __grid_constant__ XArgs A) {
+__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x_c2r(const XArgs A) {
     constexpr int M = N / 2;
     using C = FftCfg<M>;
     constexpr int P = C::P, T = C::T;
@@ -912,16 +901,6 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
     const size_t g = (size_t)blockIdx.x * CZ + col;
     const float2* src = A.spec + g;
-    if constexpr (M >= 256) {
-        if (A.pf_dist > 0 && threadIdx.x == 0) {
-            const size_t gp = ((size_t)blockIdx.x + A.pf_dist) * CZ;
-            if (gp < A.ncols) {
-#pragma unroll
-                for (int j = 0; j < M / 256; ++j) tma_prefetch_2d(&A.pf_main, (int)(gp * 2), j * 256);
-                tma_prefetch_2d(&A.pf_nyq, (int)(gp * 2), M);
-            }
-        }
-    }
     ColLayout<CZ> sl{col};
     float2 v[P];
     // each plane element is read from HBM once; the mirrored partner X[M-k] comes from the tile
@@ -1003,7 +982,7 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
 //   X[k] = 1/2 (Z[k] + conj Z[M-k]) - i/2 e^{-2 pi i k/N} (Z[k] - conj Z[M-k]),  k = 0..M
 // ---------------------------------------------------------------------------
 template <int N, int CZ>
-__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x_r2c(const __grid_constant__ XArgs A) {
+__global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x_r2c(const XArgs A) {
     constexpr int M = N / 2;
     using C = FftCfg<M>;
     constexpr int P = C::P, T = C::T;
@@ -1013,15 +992,6 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     const size_t g = (size_t)blockIdx.x * CZ + col;
     const float* src = A.field_in + g + (size_t)(2 * t) * A.ncols;
     const size_t lstride = (size_t)(2 * T) * A.ncols;
-    if constexpr (N >= 256) {
-        if (A.pf_dist > 0 && threadIdx.x == 0) {
-            const size_t gp = ((size_t)blockIdx.x + A.pf_dist) * CZ;
-            if (gp < A.ncols) {
-#pragma unroll
-                for (int j = 0; j < N / 256; ++j) tma_prefetch_2d(&A.pf_main, (int)gp, j * 256);
-            }
-        }
-    }
     float2 v[P];
 #pragma unroll
     for (int q = 0; q < P; ++q, src += lstride) v[q] = make_float2(src[0], src[A.ncols]);
