@@ -552,7 +552,7 @@ def run_multi(args, rank, world, local_rank):
     os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     mode = os.environ.get("FB_DIST_MODE", "p2p")           # p2p: exchange inside the library; nccl: all_to_all_single
-    chunks = int(os.environ.get("FB_CHUNKS", "8"))
+    chunks = int(os.environ.get("FB_CHUNKS", "16"))
     while chunks > 1 and ((N // 2) // world) % chunks:
         chunks //= 2
     flags = _lib.F_SQRTPK | _lib.F_FILTER
@@ -623,7 +623,7 @@ def run_multi(args, rank, world, local_rank):
     if mode == "p2p":
         dist.barrier()
         t_x_alone = plan.dist_bench_exchange(3) * 1e-3
-        if os.environ.get("FB_PUSH_SWEEP") and int(os.environ.get("FB_DIST_XMODE", "2")) == 2:
+        if os.environ.get("FB_PUSH_SWEEP") and int(os.environ.get("FB_DIST_XMODE", "2")) >= 2:
             # tuning: the copy kernel alone for several CTA counts per peer (collective: same order on all ranks)
             push_sweep = {}
             keep = int(os.environ.get("FB_DIST_PUSH_CTAS", "0"))
@@ -633,7 +633,7 @@ def run_multi(args, rank, world, local_rank):
                 tt = torch.tensor([plan.dist_bench_exchange(3)], device="cuda", dtype=torch.float64)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 push_sweep[str(c)] = {"ms": float(tt[0]), "GBs": a2a / (float(tt[0]) * 1e-3) / 1e9}
-            plan.dist_set_option("push_ctas", keep if keep > 0 else max(4, 48 // max(1, world - 1)))
+            plan.dist_set_option("push_ctas", keep if keep > 0 else max(4, 32 // max(1, world - 1)))
     else:
         xs = []
         for _ in range(3):
@@ -677,7 +677,10 @@ def run_multi(args, rank, world, local_rank):
                 1: "the y pass writes per-destination blocks that the copy engines push into the peers' receive buffers",
                 2: "the y pass writes per-destination blocks that a high-priority copy kernel (a few CTAs per peer, "
                    "16-byte peer stores) pushes into the peers' receive buffers while the k-space passes of the next "
-                   "chunk run"}[xmode]
+                   "chunk run",
+                3: "the y pass writes per-destination blocks that a high-priority copy kernel pushes into the peers' "
+                   "receive buffers through the bulk copy engine (cp.async.bulk, one thread per CTA) while the "
+                   "k-space passes of the next chunk run"}[xmode]
         how = ("exchange inside the library over NVLink peer memory (CUDA IPC): %s; %d chunks of planes, device-side "
                "epoch flags, no NCCL on the data path" % (mech, chunks)) if mode == "p2p" else \
               ("one NCCL all_to_all_single in %d chunks overlapped with the k-space passes" % chunks)

@@ -83,12 +83,13 @@ __global__ void __launch_bounds__(BeamGeom<N>::CT* FftCfg<N>::T) k_beam_y_r2c(co
     __syncthreads();
     const size_t kstride = (size_t)G::NZT * N * CT;  // from tile (k, zt) to tile (k+1, zt)
     float2* dst = Y + beam_tile(N, G::NZT, CT, 0, zt, N) + (size_t)x * CT + col;
+    const float2 w0 = FB_TW(tw, NF, t);               // one table load, compile-time rotations (see k_x_c2r)
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
         const float2 zk = v[q];
         const float2 zm = cconj(sm[sl((M - k) & (M - 1))]);
-        const float2 w = FB_TW(tw, NF, k);      // e^{-2 pi i k / 2N}
+        const float2 w = q == 0 ? w0 : rot_pi16(w0, q * (16 / P), -1);      // e^{-2 pi i k / 2N}
         const float2 sp = cadd(zk, zm), df = cmul(csub(zk, zm), w);
         dst[(size_t)k * kstride] = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));
         if (k == 0) dst[(size_t)M * kstride] = make_float2(zk.x - zk.y, 0.f);
@@ -181,12 +182,13 @@ __global__ void __launch_bounds__(BeamGeom<N>::CT* FftCfg<N>::T) k_beam_y_c2r(co
     float2 xnyq = make_float2(0.f, 0.f);
     if (t == 0) xnyq = src[(size_t)M * kstride];
     __syncthreads();
+    const float2 w0 = FB_TW(tw, NF, t);
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
         const float2 xk = v[q];
         const float2 xm = cconj(k == 0 ? xnyq : sm[sl(M - k)]);
-        float2 w = FB_TW(tw, NF, k);
+        float2 w = q == 0 ? w0 : rot_pi16(w0, q * (16 / P), -1);
         w.y = -w.y;
         const float2 sp = cadd(xk, xm), df = cmul(csub(xk, xm), w);
         v[q] = make_float2(sp.x - df.y, sp.y + df.x);

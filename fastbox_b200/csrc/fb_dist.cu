@@ -16,6 +16,7 @@
 #include <unistd.h>
 
 #include "fb_launch.h"
+#include "fb_tma.cuh"
 
 #define FB_DIST_MAX_CHUNKS 16
 #ifndef FB_DIST_XMODE_DEFAULT
@@ -53,6 +54,7 @@ struct fb_dist_state {
     //   2 = as 1, but a small high-priority copy kernel (k_dist_push: a few CTAs per peer, 16-byte loads, 16-byte
     //       peer stores in fully contiguous 512-byte warp requests) pushes the blocks: NVLink sees large
     //       requests instead of the 64-byte rows of the y pass tiles, and the k-space kernels keep the SMs.
+    //   3 = as 2, the copy kernel drives the bulk copy engine (cp.async.bulk) instead of the LSU.
     cudaStream_t cps[FB_MAX_RANKS];
     cudaEvent_t ev_y[FB_DIST_MAX_CHUNKS], ev_cp[FB_MAX_RANKS];
     cudaStream_t push;              // xmode 2: highest-priority stream of the copy kernel
@@ -97,6 +99,61 @@ __global__ void __launch_bounds__(512) k_dist_push(const PushArgs a) {
         for (int u = 0; u < UN; ++u) d[i + u * stride] = v[u];
     }
     for (; i < a.n16; i += stride) d[i] = __ldcs(s + i);
+}
+
+// xmode 3: the same transfer driven by ONE thread per CTA through the bulk copy engine of its SM
+// (cp.async.bulk: local HBM -> shared memory ring -> peer HBM over NVLink).  No LSU instruction, no register
+// traffic: the k-space kernels that share the SM keep their issue slots; the cost is 64 KB of shared memory.
+#define FB_PUSH_STAGES 4
+#define FB_PUSH_CHUNK 16384
+__global__ void __launch_bounds__(32) k_dist_push_tma(const PushArgs a) {
+    extern __shared__ __align__(128) unsigned char sm_push[];
+    if (threadIdx.x != 0) return;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm_push + FB_PUSH_STAGES * FB_PUSH_CHUNK);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.src[blockIdx.y]);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(a.dst[blockIdx.y]);
+    const size_t total = a.n16 * sizeof(uint4);
+    const size_t nchunks = (total + FB_PUSH_CHUNK - 1) / FB_PUSH_CHUNK;
+    // this CTA moves chunks blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long nk = nchunks > blockIdx.x ? (long)((nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+#pragma unroll
+    for (int s = 0; s < FB_PUSH_STAGES; ++s) mbar_init(&bar[s], 1);
+    mbar_fence_init();
+    auto off_of = [&](long k) { return ((size_t)blockIdx.x + (size_t)k * gridDim.x) * FB_PUSH_CHUNK; };
+    auto len_of = [&](long k) {
+        const size_t off = off_of(k);
+        return (uint32_t)(total - off < (size_t)FB_PUSH_CHUNK ? total - off : (size_t)FB_PUSH_CHUNK);
+    };
+    auto issue_load = [&](long k) {
+        const int s = (int)(k % FB_PUSH_STAGES);
+        const uint32_t len = len_of(k);
+        mbar_expect_tx(&bar[s], len);
+        bulk_load_1d(sm_push + (size_t)s * FB_PUSH_CHUNK, src + off_of(k), len, &bar[s]);
+    };
+    for (long k = 0; k < nk && k < FB_PUSH_STAGES; ++k) issue_load(k);
+    for (long k = 0; k < nk; ++k) {
+        const int s = (int)(k % FB_PUSH_STAGES);
+        mbar_wait(&bar[s], (uint32_t)((k / FB_PUSH_STAGES) & 1));
+        bulk_store_1d(dst + off_of(k), sm_push + (size_t)s * FB_PUSH_CHUNK, len_of(k));
+        tma_commit();
+        if (k >= 1 && k - 1 + FB_PUSH_STAGES < nk) {
+            tma_wait_read<1>();                              // the store of chunk k-1 has read its stage
+            issue_load(k - 1 + FB_PUSH_STAGES);
+        }
+    }
+    tma_wait_all<0>();
+}
+static int launch_push(fb_plan* p, fb_dist_state* d, const PushArgs& pa, cudaStream_t st) {
+    if (d->world <= 1) return 0;
+    if (d->xmode == 3) {
+        const size_t smem = (size_t)FB_PUSH_STAGES * FB_PUSH_CHUNK + 64;
+        if (set_smem(k_dist_push_tma, smem)) return -2;
+        k_dist_push_tma<<<dim3(d->push_ctas, d->world - 1), 32, smem, st>>>(pa);
+    } else {
+        k_dist_push<<<dim3(d->push_ctas, d->world - 1), 512, 0, st>>>(pa);
+    }
+    FB_LAUNCH_CHECK();
+    return 0;
 }
 
 // flags[d][rank] = epoch on every peer d: "everything this rank stores for step `epoch` is visible"
@@ -315,7 +372,7 @@ int fb_dist_init(fb_plan* p, int rank, int world, int with_forward) {
         int lo = 0, hi = 0;
         FB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         FB_CUDA(cudaStreamCreateWithPriority(&d->push, cudaStreamNonBlocking, hi));
-        const int dflt = world > 1 ? (48 / (world - 1) > 4 ? 48 / (world - 1) : 4) : 1;
+        const int dflt = world > 1 ? (32 / (world - 1) > 4 ? 32 / (world - 1) : 4) : 1;   // 8 GPUs: 4 per peer (measured best)
         d->push_ctas = env_int("FB_DIST_PUSH_CTAS", dflt);
     }
     d->cz_cols = env_int("FB_DIST_CZ", N >= 2048 ? 8 : 0);
@@ -458,7 +515,7 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                         reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
                 if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), vout, npl, +1, p->stream, d->cz_cols))
                     return -3;
-            } else if (d->xmode == 2) {
+            } else if (d->xmode >= 2) {
                 // y pass into local per-destination blocks (this rank's own block goes straight to its receive
                 // buffer), then the copy kernel pushes the other blocks on the high-priority stream
                 float2* send_c = d->send + (size_t)pl0 * N * N;
@@ -479,8 +536,7 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                                                              (size_t)(p->a0 + pl0) * ny * N);
                     }
                     FB_CUDA(cudaStreamWaitEvent(d->push, d->ev_y[c], 0));
-                    k_dist_push<<<dim3(d->push_ctas, d->world - 1), 512, 0, d->push>>>(pa);
-                    FB_LAUNCH_CHECK();
+                    if (launch_push(p, d, pa, d->push)) return -3;
                 }
             } else {
                 // y pass into local per-destination blocks, then one copy-engine transfer per peer
@@ -504,7 +560,7 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                 FB_CUDA(cudaEventRecord(d->ev_cp[r], d->cps[r]));
                 FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[r], 0));
             }
-        } else if (d->xmode == 2) {
+        } else if (d->xmode >= 2) {
             FB_CUDA(cudaEventRecord(d->ev_cp[0], d->push));
             FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[0], 0));
         }
@@ -559,7 +615,7 @@ int fb_dist_set_option(fb_plan* p, const char* key, int value) {
         FB_CHECK(value >= 1 && value <= 64, "push_ctas must be in 1..64");
         d->push_ctas = value;
     } else if (!strcmp(key, "xmode")) {
-        FB_CHECK(value >= 0 && value <= 2, "xmode must be 0, 1 or 2");
+        FB_CHECK(value >= 0 && value <= 3, "xmode must be 0..3");
         d->xmode = value;
     } else if (!strcmp(key, "cz_cols")) {
         d->cz_cols = value;
@@ -588,7 +644,7 @@ int fb_dist_bench_exchange(fb_plan* p, int iters, float* ms_out) {
     // xmode 2: the copy kernel alone over the whole per-destination staging array (what the pipeline pushes per step)
     PushArgs pa;
     memset(&pa, 0, sizeof(pa));
-    if (d->xmode == 2) {
+    if (d->xmode >= 2) {
         FB_CHECK(d->send != nullptr, "fb_dist_bench_exchange: run fb_dist_realise once first (staging array)");
         // blocks as laid out by a one-chunk step: [dest][plane][y'][z], na planes each
         const size_t blk = (size_t)na * ny * N;
@@ -603,11 +659,8 @@ int fb_dist_bench_exchange(fb_plan* p, int iters, float* ms_out) {
     float total = 0.f;
     for (int it = 0; it < iters + 1; ++it) {                 // first iteration = warm-up, aligns the ranks
         FB_CUDA(cudaEventRecord(p->ev[4], p->stream));
-        if (d->xmode == 2) {
-            if (d->world > 1) {
-                k_dist_push<<<dim3(d->push_ctas, d->world - 1), 512, 0, p->stream>>>(pa);
-                FB_LAUNCH_CHECK();
-            }
+        if (d->xmode >= 2) {
+            if (launch_push(p, d, pa, p->stream)) return -3;
         } else if (launch_cols_views(p, plain_view(p->work), vout, na, +1, p->stream, d->cz_cols)) {
             return -3;
         }

@@ -191,10 +191,24 @@ struct ColLayout {
     __host__ __device__ static constexpr int pstride(int S) { return (S % 16 == 0 ? S + S / 16 : S) * CZ; }
 };
 
+// a * exp(S i pi m / 16), m a compile-time constant after unrolling (the table look-up folds away)
+FB_DEV float2 rot_pi16(float2 a, int m, int S) {
+    return cmul_const(a, cos_pi16(m), (S > 0 ? 1.f : -1.f) * sin_pi16(m));
+}
+
 template <int n, int P, int R, int Ns, int S>
 FB_DEV void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
     constexpr int T = n / P;
     constexpr int B = P / R;
+    // Last stage (Ns * R == n): butterfly u of thread t has j = t + u T without wrap, so its base twiddle is
+    // w_n^t * w_P^u -- ONE table load per thread and a compile-time rotation per butterfly instead of B loads
+    // (memory-instruction slots, not arithmetic, are what these kernels run out of).
+    constexpr bool ONE_LOAD = (Ns > 1) && (Ns * R == n) && (P == 16) && (B > 1);
+    float2 wbase = make_float2(1.f, 0.f);
+    if constexpr (ONE_LOAD) {
+        wbase = FB_TW(tw, n, t);
+        if (S > 0) wbase.y = -wbase.y;
+    }
 #pragma unroll
     for (int u = 0; u < B; ++u) {
         float2 a[R];
@@ -202,17 +216,25 @@ FB_DEV void fft_stage(float2 (&v)[P], int t, const float2* __restrict__ tw) {
         for (int r = 0; r < R; ++r) a[r] = v[u + r * B];
         if constexpr (Ns > 1) {
             const int jm = (t + u * T) & (Ns - 1);
+            float2 w1;
+            if constexpr (ONE_LOAD) {
+                w1 = u == 0 ? wbase : rot_pi16(wbase, 2 * u, S);
+            } else {
+                w1 = FB_TW(tw, Ns * R, jm);
+                if (S > 0) w1.y = -w1.y;
+            }
             if constexpr (R >= 4) {
                 // twiddles w^r, r = 1..R-1, from ONE table load: powers by a product tree of depth
                 // <= 4 (each lane's R-1 twiddles are distinct, so loading them all costs ~R sector
                 // look-ups per lane in L1 -- far more than the data itself)
                 float2 w[R];
-                w[1] = FB_TW(tw, Ns * R, jm);
-                if (S > 0) w[1].y = -w[1].y;
+                w[1] = w1;
 #pragma unroll
                 for (int r = 2; r < R; ++r) w[r] = cmul(w[r / 2], w[r - r / 2]);
 #pragma unroll
                 for (int r = 1; r < R; ++r) a[r] = cmul(a[r], w[r]);
+            } else if constexpr (R == 2) {
+                a[1] = cmul(a[1], w1);
             } else {
 #pragma unroll
                 for (int r = 1; r < R; ++r) {

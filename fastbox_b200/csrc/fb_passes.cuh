@@ -918,12 +918,14 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     float2 xnyq = make_float2(0.f, 0.f);
     if (t == 0) xnyq = A.plane_off ? src[__ldg(&A.plane_off[M])] : src[(size_t)M * A.ncols];
     __syncthreads();
+    // e^{-2 pi i k/N}, k = t + T q, from ONE table load: w_N^t times the compile-time rotation e^{-i pi q/P}
+    const float2 w0 = FB_TW(A.tw, N, t);
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
         const float2 xk = v[q];
         const float2 xm = cconj(k == 0 ? xnyq : sm[sl(M - k)]);
-        float2 w = FB_TW(A.tw, N, k);
+        float2 w = q == 0 ? w0 : rot_pi16(w0, q * (16 / P), -1);
         w.y = -w.y;                                    // e^{+2 pi i k / N}
         const float2 sp = cadd(xk, xm), df = cmul(csub(xk, xm), w);
         v[q] = make_float2(sp.x - df.y, sp.y + df.x);  // sp + i*df
@@ -1005,12 +1007,13 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
         const int d = min(k >> A.per_shift, A.nranks - 1);
         return A.peer_out[d] + (size_t)(k - (d << A.per_shift)) * A.ncols + g;
     };
+    const float2 w0 = FB_TW(A.tw, N, t);               // one table load, compile-time rotations (see k_x_c2r)
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int k = t + T * q;
         const float2 zk = v[q];
         const float2 zm = cconj(sm[sl((M - k) & (M - 1))]);
-        const float2 w = FB_TW(A.tw, N, k);      // e^{-2 pi i k / N}
+        const float2 w = q == 0 ? w0 : rot_pi16(w0, q * (16 / P), -1);      // e^{-2 pi i k / N}
         const float2 sp = cadd(zk, zm), df = cmul(csub(zk, zm), w);
         // 1/2 (sp - i df)
         *plane_ptr(k) = make_float2(0.5f * (sp.x + df.y), 0.5f * (sp.y - df.x));

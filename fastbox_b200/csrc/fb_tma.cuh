@@ -57,6 +57,18 @@ template <int N>
 __device__ __forceinline__ void tma_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// 1-D bulk copies (no tensor map): global -> shared with completion on an mbarrier, shared -> global as a bulk group;
+// 16-byte aligned addresses, size a multiple of 16.  The global side may be peer memory mapped over NVLink.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
 // make generic-proxy shared-memory writes visible to the async proxy (before a TMA store reads them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -290,7 +290,7 @@ class NvlinkRealiser(object):
     (``fb_dist_*``, peer stores over NVLink).  One instance per process / GPU; every method is collective.
     """
 
-    def __init__(self, N, L, rank, world, device, group=None, with_forward=True, chunks=8):
+    def __init__(self, N, L, rank, world, device, group=None, with_forward=True, chunks=16):
         self.N, self.rank, self.world, self.chunks = N, rank, world, chunks
         self.plan = _lib.Plan(N, L[0], L[1], L[2], device)
         self.plan.dist_init(rank, world, with_forward)
