@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("FB_LIB") or os.path.join(_HERE, "libfastbox_b200.so")
 # flags / kinds (mirror include/fastbox_b200.h)
 KIND_PLAIN, KIND_VEL_X, KIND_VEL_Y, KIND_VEL_Z, KIND_POTENTIAL = 0, 1, 2, 3, 4
 F_SQRTPK, F_FILTER, F_EXP, F_ANTIHERM, F_PK, F_POLES = 1, 2, 4, 8, 16, 32
+RSD_METHODS = {"linear": 0, "nearest": 1}      # FB_RSD_LINEAR / FB_RSD_NEAREST
 MAX_EDGES = 128
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     "fb_exp_sum": (_i, [_vp, _vp, _vp, _sz, _f, C.POINTER(_d)]),
     "fb_field_moments": (_i, [_vp, _vp, _sz, C.POINTER(_d), C.POINTER(_d)]),
     "fb_rsd_remap": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp]),
+    "fb_rsd_remap_method": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _vp]),
     "fb_beam_set": (_i, [_vp, _vp]),
     "fb_beam_convolve": (_i, [_vp, _vp, _vp, _vp]),
     "fb_halo_counts": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
@@ -325,10 +327,12 @@ class Plan(object):
         check(self.lib.fb_field_moments(self.h, _ptr(field), int(n), C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def rsd_remap(self, delta, vel_z, vel_nl, zgrid, Hz, out):
+    def rsd_remap(self, delta, vel_z, vel_nl, zgrid, Hz, out, method="linear"):
         z = np.ascontiguousarray(zgrid, dtype=np.float64)
-        check(self.lib.fb_rsd_remap(self.h, _ptr(delta), _ptr(vel_z), _ptr(vel_nl), z.ctypes.data, float(Hz),
-                                    _ptr(out)))
+        if method not in RSD_METHODS:
+            raise FastBoxError("rsd_remap: method must be one of %s" % (sorted(RSD_METHODS),))
+        check(self.lib.fb_rsd_remap_method(self.h, _ptr(delta), _ptr(vel_z), _ptr(vel_nl), z.ctypes.data, float(Hz),
+                                           RSD_METHODS[method], _ptr(out)))
 
     def beam_set(self, beam):
         """Transform and keep the beam cube (float32 [N][N][N]); later beam_convolve(None, ...) calls reuse it."""

@@ -419,14 +419,15 @@ class CosmoBox(object):
     # --------------------------------------- redshift space (box.py:384-438)
     def redshift_space_density(self, delta_x=None, velocity_z=None, sigma_nl=0., method='linear'):
         """
-        Remap the density along z by the peculiar velocity (box.py:384-438).  Only ``method='linear'`` (the
-        reference's default and the only one its examples and tests use) exists on the device; the other
-        ``scipy.interpolate.griddata`` methods the reference would forward (box.py:433-437) are rejected
-        rather than silently run on the host -- this package has no CPU path.
+        Remap the density along z by the peculiar velocity (box.py:384-438).  ``method`` is the keyword the
+        reference forwards to ``scipy.interpolate.griddata`` (box.py:433-437): 'linear' (default) and 'nearest'
+        run on the device.  'cubic' is rejected: scipy's 1-D cubic is a global not-a-knot spline through the
+        sorted samples and fails on the duplicate sample that the periodic wrap of an unmoved end point
+        creates, so it has no well-defined reference result to match -- and this package has no CPU path.
         """
-        if method != 'linear':
-            raise NotImplementedError("redshift_space_density(method=%r): only 'linear' is implemented on the GPU "
-                                      "path (there is no CPU fallback)" % (method,))
+        if method not in ('linear', 'nearest'):
+            raise NotImplementedError("redshift_space_density(method=%r): 'linear' and 'nearest' are implemented "
+                                      "on the GPU path (there is no CPU fallback)" % (method,))
         N = self.N
         Hz = 100. * self.cosmo['h'] * ccl.h_over_h0(self.cosmo, self.scale_factor)  # box.py:406
         plan = self._plan
@@ -438,7 +439,7 @@ class CosmoBox(object):
             # i.e. one C-ordered (N, N, N) draw from the global generator
             vnl = plan.upload_f32(sigma_nl * np.random.normal(0., 1., (N, N, N)))
         out = plan.alloc(N ** 3 * 4)
-        plan.rsd_remap(d, v, vnl, self.z, Hz, out)
+        plan.rsd_remap(d, v, vnl, self.z, Hz, out, method=method)
         return plan.download_f64(out, (N, N, N))
 
     # ------------------------------------------------- log-normal (box.py:441-460)

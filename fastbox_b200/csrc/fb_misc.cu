@@ -113,7 +113,11 @@ struct RsdGeom {
     static constexpr size_t SMEM = (size_t)N * (8 + 2 * (4 + 4 + 4 + 4));   // t0 + 2 x (frac, y, cmax, cmin)
 };
 
-template <int N>
+// METHOD 0 = 'linear' (above); 1 = 'nearest': scipy griddata 1-D forwards to interp1d(kind='nearest',
+// fill_value='extrapolate'): the sample nearest to z_l, the half-way point going to the lower sample
+// (searchsorted(side='left') on the mid-points), the end samples outside [min s, max s] -- i.e. a choice
+// between the same two bracket samples by their distances (l - c_lo) - f_lo and (c_hi - l) + f_hi.
+template <int N, int METHOD>
 __global__ void __launch_bounds__(RsdGeom<N>::NT) k_rsd_remap(const float* __restrict__ delta,
                                                               const float* __restrict__ vel,
                                                               const float* __restrict__ vnl,
@@ -200,7 +204,15 @@ __global__ void __launch_bounds__(RsdGeom<N>::NT) k_rsd_remap(const float* __res
                     if (k != ~0u) { ih = (int)(k & LOW) - 1; chi = c; break; }
                 }
                 float r = fill;                                // outside [min s, max s]
-                if (ih >= 0) {
+                if (METHOD == 1) {
+                    if (ih >= 0 && il >= 0) {
+                        const float dlo = (float)(l - clo) - pf[il];
+                        const float dhi = (float)(chi - l) + pf[ih];
+                        r = dhi < dlo ? y[ih] : y[il];
+                    } else {
+                        r = ih >= 0 ? y[ih] : y[il];           // extrapolation = the end sample (a line has N >= 8 samples)
+                    }
+                } else if (ih >= 0) {
                     const float fh = pf[ih], yh = y[ih];
                     if (il >= 0) {
                         const float fl = pf[il], yl = y[il];
@@ -404,7 +416,14 @@ int fb_counts_to_field(fb_plan* p, const int32_t* counts, size_t n, float mul, f
 
 int fb_rsd_remap(fb_plan* p, const float* delta, const float* vel_z, const float* vel_nl, const double* zgrid,
                  double Hz, float* out) {
+    return fb_rsd_remap_method(p, delta, vel_z, vel_nl, zgrid, Hz, FB_RSD_LINEAR, out);
+}
+
+int fb_rsd_remap_method(fb_plan* p, const float* delta, const float* vel_z, const float* vel_nl,
+                        const double* zgrid, double Hz, int method, float* out) {
     FB_CUDA(cudaSetDevice(p->device));
+    FB_CHECK(method == FB_RSD_LINEAR || method == FB_RSD_NEAREST,
+             "fb_rsd_remap: method must be FB_RSD_LINEAR or FB_RSD_NEAREST");
     const int N = p->N;
     const size_t n3 = (size_t)N * N * N;
     FB_CHECK(delta && vel_z && zgrid && out, "fb_rsd_remap: NULL buffer");
@@ -421,7 +440,7 @@ int fb_rsd_remap(fb_plan* p, const float* delta, const float* vel_z, const float
     const unsigned ctas = (unsigned)((nlines + FB_RSD_LPC - 1) / FB_RSD_LPC);
 #define FB_RSD(N_)                                                                                         \
     {                                                                                                      \
-        auto kern = k_rsd_remap<N_>;                                                                       \
+        auto kern = method == FB_RSD_NEAREST ? k_rsd_remap<N_, 1> : k_rsd_remap<N_, 0>;                    \
         if (set_smem(kern, RsdGeom<N_>::SMEM)) return -2;                                                  \
         kern<<<ctas, RsdGeom<N_>::NT, RsdGeom<N_>::SMEM, p->stream>>>(                                     \
             (const float*)dd, (const float*)dv, (const float*)dn, (const double*)p->aux, Hz, (float*)dout, \

@@ -163,6 +163,15 @@ int fb_field_moments(fb_plan* plan, const float* field, size_t n, double* sum, d
 /* z[N] grid coordinates (host, float64); vel_nl nullable (sigma_nl * N(0,1)).  */
 int fb_rsd_remap(fb_plan* plan, const float* delta, const float* vel_z, const float* vel_nl, const double* zgrid,
                  double Hz, float* out);
+/* the `method` keyword the reference forwards to scipy.interpolate.griddata (box.py:403-405, 433-437):
+ * FB_RSD_LINEAR = 'linear' (fb_rsd_remap), FB_RSD_NEAREST = 'nearest' (nearest sample, half-way points go to
+ * the lower sample, end samples beyond the range).  'cubic' is not offered: scipy's 1-D cubic is a global
+ * not-a-knot spline through the sorted samples, which rejects the duplicate sample that the periodic wrap of
+ * an unmoved end point creates (s_{N-1} -> z_0), so the reference itself fails on it for small velocities. */
+#define FB_RSD_LINEAR 0
+#define FB_RSD_NEAREST 1
+int fb_rsd_remap_method(fb_plan* plan, const float* delta, const float* vel_z, const float* vel_nl,
+                        const double* zgrid, double Hz, int method, float* out);
 
 /* ---- beam convolution: beams.py:81-87 ----------------------------------------- */
 /* out = fftconvolve(beam, field, mode='same', axes=[0,1]) / sum_xy beam  per channel z.

@@ -160,10 +160,32 @@ def run_cube():
     return out
 
 
+def run_rsd_methods():
+    """redshift_space_density(method='nearest') of the unmodified reference (box.py:403-405, 433-437) on the
+    inputs already held by the per-case fixtures (their log-normal field and v_z), without and with sigma_nl."""
+    box_m = ref_loader.load("box")
+    out = {}
+    for c in CASES:
+        g = np.load(os.path.join(ROOT, "tests", "golden", c["name"] + ".npz"))
+        box = box_m.CosmoBox(cosmo=box_m.default_cosmo, box_scale=c["scale"], nsamp=c["N"],
+                             redshift=c["redshift"], realise_now=False)
+        out[c["name"] + "_nearest0"] = box.redshift_space_density(delta_x=g["lognormal"], velocity_z=g["vel_z"],
+                                                                  sigma_nl=0., method="nearest")
+        np.random.seed(c["seed"] + 100)
+        out[c["name"] + "_nearest120"] = box.redshift_space_density(delta_x=g["lognormal"], velocity_z=g["vel_z"],
+                                                                    sigma_nl=120., method="nearest")
+    return out
+
+
 def main():
     warnings.simplefilter("ignore")
     dest = os.path.join(ROOT, "tests", "golden")
     os.makedirs(dest, exist_ok=True)
+    if "--rsd-methods" in sys.argv:                     # needs the per-case fixtures: with --all it runs last
+        path = os.path.join(dest, "rsd_methods.npz")
+        np.savez_compressed(path, **run_rsd_methods())
+        print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024.))
+        return
     if "--cube" in sys.argv or "--all" in sys.argv:
         path = os.path.join(dest, "fg_noise_cube.npz")
         np.savez_compressed(path, **run_cube())
@@ -180,6 +202,10 @@ def main():
         out = run_case(c)
         path = os.path.join(dest, c["name"] + ".npz")
         np.savez_compressed(path, **out)
+        print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024.))
+    if "--all" in sys.argv:
+        path = os.path.join(dest, "rsd_methods.npz")
+        np.savez_compressed(path, **run_rsd_methods())
         print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024.))
 
 

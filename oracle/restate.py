@@ -534,7 +534,7 @@ def correlation_function_port(field_a, N, Lx, Ly, Lz, edges, field_b=None):
 #   scipy griddata 1-D linear == argsort + interp1d(linear, fill_value)
 #   (scipy/interpolate/_ndgriddata.py:315-330, _interpolate.py:491-518,592-593)
 # --------------------------------------------------------------------------
-def rsd_remap_line(z, dens, vel_total, Hz):
+def rsd_remap_line(z, dens, vel_total, Hz, method="linear"):
     s = z - vel_total / Hz                                        # box.py:422
     zmin = np.min(z)
     length = np.max(z) - zmin
@@ -543,6 +543,14 @@ def rsd_remap_line(z, dens, vel_total, Hz):
     order = np.argsort(s)
     xs = s[order]
     ys = dens[order]
+    if method == "nearest":
+        # griddata 1-D 'nearest' = interp1d(kind='nearest', fill_value='extrapolate'): mid-points
+        # x/2 + x/2 and searchsorted(side='left') (scipy/interpolate/_interpolate.py: _call_nearest)
+        half = xs / 2.0
+        bds = half[1:] + half[:-1]
+        return ys[np.searchsorted(bds, z, side="left").clip(0, xs.size - 1)]
+    if method != "linear":
+        raise ValueError("rsd_remap_line: method %r" % (method,))
     hi = np.searchsorted(xs, z).clip(1, xs.size - 1)
     lo = hi - 1
     with np.errstate(all="ignore"):
@@ -552,13 +560,13 @@ def rsd_remap_line(z, dens, vel_total, Hz):
     return out
 
 
-def redshift_space_density(delta_x, velocity_z, z, Hz, vel_nl=None):
+def redshift_space_density(delta_x, velocity_z, z, Hz, vel_nl=None, method="linear"):
     """vel_nl: optional (N,N,N) array = sigma_nl * N(0,1) drawn line by line (box.py:418)."""
     out = np.empty_like(delta_x)
     for i in range(delta_x.shape[0]):
         for j in range(delta_x.shape[1]):
             v = velocity_z[i, j, :] + (0. if vel_nl is None else vel_nl[i, j, :])
-            out[i, j, :] = rsd_remap_line(z, delta_x[i, j, :], v, Hz)
+            out[i, j, :] = rsd_remap_line(z, delta_x[i, j, :], v, Hz, method)
     return out
 
 

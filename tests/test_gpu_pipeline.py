@@ -226,6 +226,35 @@ def test_rsd_remap_golden(gpu, name):
     plan.close()
 
 
+@pytest.mark.parametrize("name", ["n16_cubic", "n16_cuboid", "n32_gpc"])
+def test_rsd_remap_nearest_golden(gpu, name):
+    """method='nearest' (box.py:403-405, 433-437) picks input values: every output equals the unmodified
+    reference's float64 result rounded to float32, except where rounding the velocities to float32 (or the
+    float32 in-cell fraction) flips a near-tie between the two neighbouring samples -- counted below."""
+    g, gm = load_golden(name), load_golden("rsd_methods")
+    N, L = int(g["N"]), _case_L(g)
+    plan = _lib.Plan(N, *L)
+    out = np.empty((N, N, N), np.float32)
+    d32 = g["lognormal"].astype(np.float32)
+    v32 = g["vel_z"].astype(np.float32)
+    plan.rsd_remap(d32, v32, None, g["z_grid"], float(g["Hz"]), out, method="nearest")
+    ref32 = R.redshift_space_density(d32.astype(np.float64), v32.astype(np.float64), g["z_grid"], float(g["Hz"]),
+                                     method="nearest")
+    nflip = int(np.count_nonzero(out != ref32.astype(np.float32)))
+    nflip_ref = int(np.count_nonzero(out != gm[name + "_nearest0"].astype(np.float32)))
+    print("rsd nearest %s: %d / %d voxels differ from the oracle, %d from the reference" % (name, nflip, N ** 3, nflip_ref))
+    assert nflip <= 2 and nflip_ref <= 2
+    np.random.seed(int(g["seed"]) + 100)
+    vnl = (120. * np.random.normal(0., 1., (N, N, N))).astype(np.float32)
+    plan.rsd_remap(d32, v32, vnl, g["z_grid"], float(g["Hz"]), out, method="nearest")
+    ref32 = R.redshift_space_density(d32.astype(np.float64), v32.astype(np.float64), g["z_grid"], float(g["Hz"]),
+                                     vnl.astype(np.float64), method="nearest")
+    assert int(np.count_nonzero(out != ref32.astype(np.float32))) <= 2
+    with pytest.raises(_lib.FastBoxError):
+        plan.rsd_remap(d32, v32, None, g["z_grid"], float(g["Hz"]), out, method="cubic")
+    plan.close()
+
+
 @pytest.mark.parametrize("lognormal", [False, True])
 def test_halo_counts_bit_exact(gpu, lognormal):
     g = load_golden("n32_gpc")

@@ -53,6 +53,12 @@ def test_port_reproduces_reference_golden(name):
         vnl = 120. * np.random.normal(0., 1., (N, N, N))
         rs = R.redshift_space_density(g["lognormal"], g["vel_z"], g["z_grid"], float(g["Hz"]), vnl)
         assert np.allclose(rs, g["rsd120"], rtol=1e-13, atol=1e-13)
+        # method='nearest' (box.py:403-405): a selection of input values, so bit-for-bit
+        gm = load_golden("rsd_methods")
+        rs = R.redshift_space_density(g["lognormal"], g["vel_z"], g["z_grid"], float(g["Hz"]), method="nearest")
+        assert np.array_equal(rs, gm[name + "_nearest0"])
+        rs = R.redshift_space_density(g["lognormal"], g["vel_z"], g["z_grid"], float(g["Hz"]), vnl, method="nearest")
+        assert np.array_equal(rs, gm[name + "_nearest120"])
         from _util import DEFAULT_COSMO  # noqa: F401
         bc = R.convolve_fft(__import__("oracle.make_golden", fromlist=["beam_cube"]).beam_cube(N), g["rsd0"])
         assert np.allclose(bc, g["beam_conv"], rtol=1e-12, atol=1e-14)
