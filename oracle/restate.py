@@ -435,7 +435,10 @@ def binned_power_spectrum_lean(half_a, N, Lx, Ly, Lz, nbins=20, kbins=None, half
 
 def pk_multipoles(half, N, Lx, Ly, Lz, nbins=20, kbins=None, ells=(0, 2, 4)):
     """
-    PARITY UNPINNED (reference uses nbodykit FFTPower, example_box.py:48-52).
+    PARITY UNPINNED w.r.t. nbodykit (the reference uses its FFTPower, example_box.py:48-52; absent here).
+    Tied instead to the published Kaiser / Hamilton multipoles of (1 + beta mu^2)^2 P(k) -- which fix the (2l+1)
+    factor, the Legendre polynomials and the line of sight -- in
+    tests/test_oracle_cpu.py::test_multipoles_and_cross_power_known_answers.
     P_l(k) = (2l+1) < |d_k|^2 L_l(mu) >_bin / boxfactor, mu = k_z/|k|, LOS = z,
     same bins / weights as ``binned_power_spectrum_lean``.
     """

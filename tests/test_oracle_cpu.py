@@ -290,3 +290,60 @@ def test_two_point_restatements_are_self_consistent():
     assert abs(xi[0] - np.mean(f * f)) < 1e-12 and c[1] == 1      # the zero lag alone sits in the first bin
     sel = (r >= 7.0) & (r < 11.0)
     assert abs(xi[2] - full[sel].mean()) < 1e-13 and c[3] == sel.sum()
+
+
+def test_multipoles_and_cross_power_known_answers():
+    """
+    The multipole and cross-power restatements cannot be pinned to nbodykit (absent), so they are tied to
+    published known answers instead.  (1) Kaiser (1987) / Hamilton (1992): a spectrum d_s(k) = (1 + beta mu^2) d(k)
+    with mu = k_z / |k| has P_0 / P = 1 + 2 beta/3 + beta^2/5, P_2 / P = 4 beta/3 + 4 beta^2/7, P_4 / P = 8 beta^2/35 --
+    this fixes the (2l+1) normalisation, the Legendre polynomials and the line of sight (z) of `pk_multipoles`.
+    (2) cross(a, c a) = c auto(a) with the pinned auto estimator, cross(a, b) = cross(b, a), and the cross power of a
+    field with a copy shifted by one cell along x carries the factor cos(k_x dx).
+    """
+    N, L = 128, (5e2, 5e2, 5e2)
+    rng = np.random.default_rng(5)
+    f = rng.standard_normal((N, N, N))
+    half = R.rfft3_axis0(f)
+    half = half / np.maximum(np.abs(half), 1e-300) * np.sqrt(R.boxfactor(N, *L))      # |d_k|^2 / boxfactor = 1 exactly
+    m = R.mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    kk = np.sqrt(m[:h, None, None] ** 2 + m[None, :, None] ** 2 + m[None, None, :] ** 2)
+    with np.errstate(all="ignore"):
+        mu = np.where(kk > 0, m[None, None, :] / kk, 0.0)
+    beta = 0.6
+    knyq = np.pi * N / L[0]
+    edges = np.linspace(0.3 * knyq, 0.98 * knyq, 5)            # complete, well-populated shells inside the Nyquist cube
+    cent, poles = R.pk_multipoles(half * (1.0 + beta * mu ** 2), N, *L, kbins=edges)
+    want = {0: 1 + 2 * beta / 3 + beta ** 2 / 5, 2: 4 * beta / 3 + 4 * beta ** 2 / 7, 4: 8 * beta ** 2 / 35}
+    # tolerance = the quadrature error of the discrete shells (falls as 1/N^2: 1.6e-4 / 5.5e-3 / 3.7e-2 at N = 64)
+    for ell, tol in ((0, 2e-4), (2, 3e-3), (4, 1.5e-2)):
+        assert np.all(np.abs(poles[ell] - want[ell]) < tol), (ell, poles[ell], want[ell])
+    # an isotropic spectrum has no quadrupole / hexadecapole beyond the discreteness of the shells
+    _, iso = R.pk_multipoles(half, N, *L, kbins=edges)
+    assert np.all(np.abs(iso[0] - 1.0) < 1e-12) and np.all(np.abs(iso[2]) < 3e-3) and np.all(np.abs(iso[4]) < 1.5e-2)
+
+    N = 32
+    m = R.mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    f = rng.standard_normal((N, N, N))
+    g = rng.standard_normal((N, N, N))
+    ha, hb = R.rfft3_axis0(f), R.rfft3_axis0(g)
+    kc, auto, aerr, acnt = R.binned_power_spectrum_lean(ha, N, *L, nbins=20)
+    kc2, cr, cerr, ccnt = R.binned_power_spectrum_lean(ha, N, *L, nbins=20, half_b=2.5 * ha)
+    ok = ~np.isnan(auto)
+    assert np.array_equal(acnt, ccnt) and np.allclose(cr[ok], 2.5 * auto[ok], rtol=1e-13)
+    ab = R.binned_power_spectrum_lean(ha, N, *L, nbins=20, half_b=hb)[1]
+    ba = R.binned_power_spectrum_lean(hb, N, *L, nbins=20, half_b=ha)[1]
+    assert np.allclose(ab[ok], ba[ok], rtol=0, atol=1e-12 * np.abs(auto[ok]).max())
+    shifted = R.rfft3_axis0(np.roll(f, 1, axis=0))             # f(x - dx): spectrum times exp(-i k_x dx)
+    power = (ha * np.conj(ha)).real * np.cos(2 * np.pi * m[:h] / N)[:, None, None]
+    bins = R.pk_bin_edges(N, *L, 20, None)
+    idx = R.digitize_half(N, *L, bins)
+    w = np.broadcast_to(R.half_weights(N)[:, None, None], power.shape)
+    s = np.bincount(idx.ravel(), weights=(w * power).ravel(), minlength=bins.size + 1)
+    c = np.bincount(idx.ravel(), weights=w.ravel(), minlength=bins.size + 1)
+    with np.errstate(all="ignore"):
+        want_x = (s / c)[1:bins.size] / R.boxfactor(N, *L)
+    got_x = R.binned_power_spectrum_lean(ha, N, *L, nbins=20, half_b=shifted)[1]
+    assert np.allclose(got_x[ok], want_x[ok], rtol=1e-10, atol=1e-12 * np.abs(auto[ok]).max())
