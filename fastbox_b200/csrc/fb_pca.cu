@@ -102,6 +102,112 @@ __global__ void __launch_bounds__(256) k_pca_cov(const double* __restrict__ x, c
         }
 }
 
+// k_pca_cov128: the same contraction on 128 x 128 tiles with 8 x 8 float64 accumulators per thread.
+// The 4 x 4 kernel above reads 8 shared-memory words for 16 FMAs, which keeps the shared-memory pipe exactly as
+// busy as the FP64 pipe (64 wavefronts against 64 FMA cycles per k and CTA), and its panels are loaded, stored
+// and consumed in sequence.  Here a thread reads its 8 + 8 operands as eight 16-byte loads for 64 FMAs (lanes of
+// a warp form an 8 x 4 patch, so one load instruction touches at most 128 contiguous bytes: 8 wavefronts for 2048
+// FMAs), the next panel of KT pixels is fetched into registers while the current one is consumed (one barrier per
+// panel, two shared-memory buffers), and the cube goes through L2 nine times instead of seventeen.  Output element
+// (i, j) of a thread: f = f0 + 2 ty + (i & 1) + 32 (i >> 1), g = g0 + 2 tx + (j & 1) + 32 (j >> 1).  Diagonal
+// tiles skip their lower-left 64 x 64 quadrant (never read by k_pca_cov_finish).  nf must be even (16-byte loads).
+template <int KT>
+__global__ void __launch_bounds__(256, 1) k_pca_cov128(const double* __restrict__ x, const double* __restrict__ mean,
+                                                        int nf, size_t npix, int ntile, double* __restrict__ cov) {
+    constexpr int TL = 128;
+    constexpr int RPT = KT / 4;                                      // panel rows per loader thread
+    extern __shared__ __align__(16) unsigned char pca_cov_smem[];
+    double (*sa)[KT][TL] = reinterpret_cast<double (*)[KT][TL]>(pca_cov_smem);                 // [2][KT][TL]
+    double (*sb)[KT][TL] = reinterpret_cast<double (*)[KT][TL]>(pca_cov_smem + 2 * sizeof(double) * KT * TL);
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= ntile - ti) {
+        rem -= ntile - ti;
+        ++ti;
+    }
+    const int tj = ti + rem;
+    const bool diag = ti == tj;
+    const int f0 = ti * TL, g0 = tj * TL;
+    const size_t per_slice = ((npix + gridDim.y - 1) / gridDim.y + KT - 1) / KT * KT;
+    const size_t p0 = (size_t)blockIdx.y * per_slice;
+    const size_t p1 = p0 + per_slice < npix ? p0 + per_slice : npix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = (lane & 7) + 8 * (warp & 1), ty = (lane >> 3) + 4 * (warp >> 1);   // 16 x 16 threads
+    const int lc = 2 * (threadIdx.x & 63), lr = threadIdx.x >> 6;                     // loader: channel pair, row 0..3
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    const bool oka = f0 + lc < nf, okb = g0 + lc < nf;
+    double2 ma = make_double2(0.0, 0.0), mb = ma;
+    if (oka) ma = *reinterpret_cast<const double2*>(mean + f0 + lc);
+    if (okb) mb = *reinterpret_cast<const double2*>(mean + g0 + lc);
+    double2 ra[RPT], rb[RPT];
+    auto fetch = [&](size_t pb) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const size_t p = pb + lr + 4 * r;
+            ra[r] = make_double2(0.0, 0.0);
+            rb[r] = make_double2(0.0, 0.0);
+            if (p < p1) {
+                const double* row = x + p * (size_t)nf;
+                if (oka) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(row + f0 + lc));
+                    ra[r] = make_double2(v.x - ma.x, v.y - ma.y);
+                }
+                if (okb) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(row + g0 + lc));
+                    rb[r] = make_double2(v.x - mb.x, v.y - mb.y);
+                }
+            }
+        }
+    };
+    auto park = [&](int b) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            *reinterpret_cast<double2*>(&sa[b][lr + 4 * r][lc]) = ra[r];
+            *reinterpret_cast<double2*>(&sb[b][lr + 4 * r][lc]) = rb[r];
+        }
+    };
+    if (p0 < p1) {
+        fetch(p0);
+        park(0);
+    }
+    __syncthreads();
+    int cur = 0;
+    for (size_t pb = p0; pb < p1; pb += KT, cur ^= 1) {
+        const bool more = pb + KT < p1;
+        if (more) fetch(pb + KT);                                   // in flight while this panel is consumed
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            double a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 va = *reinterpret_cast<const double2*>(&sa[cur][k][2 * ty + 32 * i]);
+                const double2 vb = *reinterpret_cast<const double2*>(&sb[cur][k][2 * tx + 32 * i]);
+                a[2 * i] = va.x;
+                a[2 * i + 1] = va.y;
+                b[2 * i] = vb.x;
+                b[2 * i + 1] = vb.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (!(diag && i >= 4 && j < 4)) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        if (more) park(cur ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int f = f0 + 2 * ty + (i & 1) + 32 * (i >> 1), g = g0 + 2 * tx + (j & 1) + 32 * (j >> 1);
+            if (f < nf && g < nf && !(diag && i >= 4 && j < 4)) atomicAdd(&cov[(size_t)f * nf + g], acc[i][j]);
+        }
+}
+
 // (An FP64 tensor-core variant of this kernel -- mma.sync m8n8k4 on the same tiles -- was measured at 99 ms against
 // 88 ms for the SIMT kernel at 1024^3 and removed: the limit is not the FP64 pipe, see profiles/README.md.)
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {      // fb_bench_fp64 probe
@@ -277,15 +383,41 @@ int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* 
         FB_LAUNCH_CHECK();
     }
     FB_CUDA(cudaMemsetAsync(d_cov, 0, (size_t)nf * nf * sizeof(double), p->stream));
-    const int ntile = (nf + PCA_TILE - 1) / PCA_TILE;
-    const int ntri = ntile * (ntile + 1) / 2;
-    // ~4 full waves at 3 resident CTAs per SM (a grid of 1.5 waves left the second one half empty)
-    int slices = (p->sm_count * 12 + ntri / 2) / ntri;
-    const size_t max_slices = (npix + PCA_KT - 1) / PCA_KT;
-    if ((size_t)slices > max_slices) slices = (int)max_slices;
-    if (slices < 1) slices = 1;
-    k_pca_cov<<<dim3(ntri, slices), 256, 0, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
-    FB_LAUNCH_CHECK();
+    // 128 x 128 tiles (k_pca_cov128) from 256 channels on; FB_PCA_TILE=64 keeps the 64 x 64 kernel, FB_PCA_KT the panel depth
+    const int tile_opt = env_int("FB_PCA_TILE", nf >= 256 && nf % 2 == 0 ? 128 : 64);
+    if (tile_opt == 128 && nf % 2 == 0) {
+        const int kt = env_int("FB_PCA_KT", 8);
+        FB_CHECK(kt == 8 || kt == 16, "FB_PCA_KT must be 8 or 16");
+        const int ntile = (nf + 127) / 128;
+        const int ntri = ntile * (ntile + 1) / 2;
+        // one resident CTA per SM: a whole number of waves (the diagonal tiles finish a quarter earlier)
+        int waves = env_int("FB_PCA_WAVES", 9);
+        int slices = (p->sm_count * waves + ntri / 2) / ntri;
+        const size_t max_slices = (npix + 4 * kt - 1) / (4 * kt);
+        if ((size_t)slices > max_slices) slices = (int)max_slices;
+        if (slices < 1) slices = 1;
+        const size_t smem = 4 * sizeof(double) * kt * 128;
+        if (kt == 8) {
+            auto kern = k_pca_cov128<8>;
+            if (set_smem(kern, smem)) return -2;
+            kern<<<dim3(ntri, slices), 256, smem, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
+        } else {
+            auto kern = k_pca_cov128<16>;
+            if (set_smem(kern, smem)) return -2;
+            kern<<<dim3(ntri, slices), 256, smem, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
+        }
+        FB_LAUNCH_CHECK();
+    } else {
+        const int ntile = (nf + PCA_TILE - 1) / PCA_TILE;
+        const int ntri = ntile * (ntile + 1) / 2;
+        // ~4 full waves at 3 resident CTAs per SM (a grid of 1.5 waves left the second one half empty)
+        int slices = (p->sm_count * 12 + ntri / 2) / ntri;
+        const size_t max_slices = (npix + PCA_KT - 1) / PCA_KT;
+        if ((size_t)slices > max_slices) slices = (int)max_slices;
+        if (slices < 1) slices = 1;
+        k_pca_cov<<<dim3(ntri, slices), 256, 0, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
+        FB_LAUNCH_CHECK();
+    }
     k_pca_cov_finish<<<dim3((nf + 255) / 256, nf), 256, 0, p->stream>>>(d_cov, nf, 1.0 / (double)(npix - 1));
     FB_LAUNCH_CHECK();
     FB_CUDA(cudaMemcpyAsync(cov_out, d_cov, (size_t)nf * nf * sizeof(double), cudaMemcpyDefault, p->stream));
