@@ -147,26 +147,22 @@ __global__ void __launch_bounds__(256, 1) k_pca_cov128(const double* __restrict_
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const size_t p = pb + lr + 4 * r;
-            ra[r] = make_double2(0.0, 0.0);
-            rb[r] = make_double2(0.0, 0.0);
+            ra[r] = ma;
+            rb[r] = mb;
             if (p < p1) {
                 const double* row = x + p * (size_t)nf;
-                if (oka) {
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(row + f0 + lc));
-                    ra[r] = make_double2(v.x - ma.x, v.y - ma.y);
-                }
-                if (okb) {
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(row + g0 + lc));
-                    rb[r] = make_double2(v.x - mb.x, v.y - mb.y);
-                }
+                // raw values: the mean is subtracted in park(), after the panel in between has been consumed, so that
+                // nothing waits on these loads before the FMA block (out-of-range lanes hold the mean itself -> 0)
+                if (oka) ra[r] = __ldg(reinterpret_cast<const double2*>(row + f0 + lc));
+                if (okb) rb[r] = __ldg(reinterpret_cast<const double2*>(row + g0 + lc));
             }
         }
     };
     auto park = [&](int b) {
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            *reinterpret_cast<double2*>(&sa[b][lr + 4 * r][lc]) = ra[r];
-            *reinterpret_cast<double2*>(&sb[b][lr + 4 * r][lc]) = rb[r];
+            *reinterpret_cast<double2*>(&sa[b][lr + 4 * r][lc]) = make_double2(ra[r].x - ma.x, ra[r].y - ma.y);
+            *reinterpret_cast<double2*>(&sb[b][lr + 4 * r][lc]) = make_double2(rb[r].x - mb.x, rb[r].y - mb.y);
         }
     };
     if (p0 < p1) {
@@ -386,7 +382,7 @@ int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* 
     // 128 x 128 tiles (k_pca_cov128) from 256 channels on; FB_PCA_TILE=64 keeps the 64 x 64 kernel, FB_PCA_KT the panel depth
     const int tile_opt = env_int("FB_PCA_TILE", nf >= 256 && nf % 2 == 0 ? 128 : 64);
     if (tile_opt == 128 && nf % 2 == 0) {
-        const int kt = env_int("FB_PCA_KT", 8);
+        const int kt = env_int("FB_PCA_KT", 16);
         FB_CHECK(kt == 8 || kt == 16, "FB_PCA_KT must be 8 or 16");
         const int ntile = (nf + 127) / 128;
         const int ntri = ntile * (ntile + 1) / 2;

@@ -126,6 +126,20 @@ def test_c_oracle_matches_numpy_restatement():
                           ctypes.c_long(lam.size), out.ctypes.data_as(ctypes.c_void_p))
     ref = R.poisson_from_uniform(lam, u)
     assert np.array_equal(out.astype(np.int64), ref)
+    # the certain-zero shortcut of the header (u < (1 - lam) - 1e-14 for lam < 0.5) never changes a count: uniforms
+    # placed on and around its threshold and around p_0 = exp(-lam), sparse-tracer means (the NumPy restatement
+    # has no shortcut)
+    lam_s = np.concatenate([rng.uniform(0, 0.5, 20000), 10.0 ** rng.uniform(-12, -1, 20000), [0.5, 0.49999999999999994]])
+    thr = (1.0 - lam_s) - 1e-14
+    p0 = R._exp_neg(lam_s)
+    cases = [thr, np.nextafter(thr, 0.0), np.nextafter(thr, 2.0), p0, np.nextafter(p0, 0.0), np.nextafter(p0, 2.0),
+             1.0 - lam_s, np.minimum(p0 + lam_s * rng.random(lam_s.size), np.nextafter(1.0, 0.0)), rng.random(lam_s.size)]
+    for us in cases:
+        us = np.ascontiguousarray(np.clip(us, 0.0, np.nextafter(1.0, 0.0)))
+        outs = np.zeros(lam_s.size, np.int32)
+        lib.fb_oracle_poisson(lam_s.ctypes.data_as(ctypes.c_void_p), us.ctypes.data_as(ctypes.c_void_p),
+                              ctypes.c_long(lam_s.size), outs.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(outs.astype(np.int64), R.poisson_from_uniform(lam_s, us))
     # distributional sanity vs np.random.poisson (the reference's sampler, halos.py:116)
     lam1 = np.full(200000, 7.5)
     k = R.poisson_from_uniform(lam1, rng.random(lam1.size))
