@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "Mcells/s realise+filter+P(k)"
+DIST_XMODE_DEFAULT = 2   # exchange mechanism of the sharded run (fb_dist.cu); FB_DIST_XMODE overrides
 BYTES_PER_CELL_HBM_NOISE = 28.0      # 8+4, 4+4, 4+4  
 BYTES_PER_CELL_PHILOX = 20.0         # 0+4, 4+4, 4+4
 PASS1_BYTES_PER_CELL = {"hbm": 12.0, "philox": 4.0}
@@ -606,6 +607,38 @@ def run_multi(args, rank, world, local_rank):
     launches = _lib.launch_count() - launches0
     pass_ms /= args.steps
 
+    # tuning / evidence: other exchange mechanisms measured in the same run (FB_DIST_COMPARE="2,4:2,4:3" = xmode or
+    # xmode:h1_every), same steps, max over ranks; each is checked against the default's field moments
+    alternatives = None
+    if mode == "p2p" and os.environ.get("FB_DIST_COMPARE"):
+        alternatives = []
+        base_mode = int(os.environ.get("FB_DIST_XMODE", str(DIST_XMODE_DEFAULT)))
+        _, _, sums0 = dr.realise(0, flags, want_pk=True, want_sums=True)
+        for spec in os.environ["FB_DIST_COMPARE"].split(","):
+            xm, _, he = spec.partition(":")
+            plan.dist_set_option("xmode", int(xm))
+            if he:
+                plan.dist_set_option("h1_every", int(he))
+            _, pk_a, sums_a = dr.realise(0, flags, want_pk=True, want_sums=True)
+            step(1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for s_ in range(args.steps):
+                step(s_)
+            b.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([a.elapsed_time(b) / args.steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            same = abs(sums_a[0] - sums0[0]) <= 1e-9 * abs(sums0[1]) ** 0.5 + 1e-9 * abs(sums0[0]) and \
+                abs(sums_a[1] - sums0[1]) <= 1e-10 * abs(sums0[1])
+            alternatives.append({"xmode": int(xm), "h1_every": int(he) if he else None, "ms_per_step": float(tt[0]),
+                                 "field_moments_equal_default": bool(same),
+                                 "pk_count_sum_ok": bool(int(pk_a["count"].sum()) == N ** 3)})
+        plan.dist_set_option("xmode", base_mode)
+
     # result checks on the full-size box itself: every mode binned once, Parseval (box.py:944-946)
     if mode == "p2p":
         _, pk, sums = dr.realise(0, flags, want_pk=True, want_sums=True)
@@ -623,7 +656,7 @@ def run_multi(args, rank, world, local_rank):
     if mode == "p2p":
         dist.barrier()
         t_x_alone = plan.dist_bench_exchange(3) * 1e-3
-        if os.environ.get("FB_PUSH_SWEEP") and int(os.environ.get("FB_DIST_XMODE", "2")) >= 2:
+        if os.environ.get("FB_PUSH_SWEEP") and int(os.environ.get("FB_DIST_XMODE", str(DIST_XMODE_DEFAULT))) >= 2:
             # tuning: the copy kernel alone for several CTA counts per peer (collective: same order on all ranks)
             push_sweep = {}
             keep = int(os.environ.get("FB_DIST_PUSH_CTAS", "0"))
@@ -672,8 +705,12 @@ def run_multi(args, rank, world, local_rank):
         nv = a2a / t_x_alone / 1e9
         check = dict(check or {}, count_sum=int(pk["count"].sum()), count_sum_expected=N ** 3,
                      count_sum_ok=bool(int(pk["count"].sum()) == N ** 3), parseval_ratio=parseval)
-        xmode = int(os.environ.get("FB_DIST_XMODE", "2"))
-        mech = {0: "the y pass stores straight into the peers' receive buffers",
+        xmode = int(os.environ.get("FB_DIST_XMODE", str(DIST_XMODE_DEFAULT)))
+        mech = {4: "the y pass writes per-destination blocks that a high-priority copy kernel (a few CTAs per peer, "
+                   "16-byte peer stores) pushes into the peers' receive buffers while the k-space passes of the next "
+                   "chunk run; the z axis is split in two halves, first halves are sent first and announced by their "
+                   "own epoch flags, so the x pass of the first half of the columns overlaps the rest of the exchange",
+                0: "the y pass stores straight into the peers' receive buffers",
                 1: "the y pass writes per-destination blocks that the copy engines push into the peers' receive buffers",
                 2: "the y pass writes per-destination blocks that a high-priority copy kernel (a few CTAs per peer, "
                    "16-byte peer stores) pushes into the peers' receive buffers while the k-space passes of the next "
@@ -684,7 +721,7 @@ def run_multi(args, rank, world, local_rank):
         how = ("exchange inside the library over NVLink peer memory (CUDA IPC): %s; %d chunks of planes, device-side "
                "epoch flags, no NCCL on the data path" % (mech, chunks)) if mode == "p2p" else \
               ("one NCCL all_to_all_single in %d chunks overlapped with the k-space passes" % chunks)
-        nvlink = {"bytes_sent_per_gpu": a2a, "exchange_alone_ms": t_x_alone * 1e3, "achieved_GBs": nv, "push_sweep": push_sweep,
+        nvlink = {"alternatives": alternatives, "bytes_sent_per_gpu": a2a, "exchange_alone_ms": t_x_alone * 1e3, "achieved_GBs": nv, "push_sweep": push_sweep,
                   "frac_of_900": nv / 900.0, "frac_of_measured_770": nv / 770.0, "mode": mode}
         if mode == "p2p":
             nvlink.update({"in_pipeline": {"kspace_passes_with_peer_stores_ms": pass_ms[0], "wait_for_peers_ms": pass_ms[1],
