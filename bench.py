@@ -607,8 +607,8 @@ def run_multi(args, rank, world, local_rank):
     launches = _lib.launch_count() - launches0
     pass_ms /= args.steps
 
-    # tuning / evidence: other exchange mechanisms measured in the same run (FB_DIST_COMPARE="2,4:2,4:3" = xmode or
-    # xmode:h1_every), same steps, max over ranks; each is checked against the default's field moments
+    # tuning / evidence: other exchange mechanisms measured in the same run (FB_DIST_COMPARE="1,3,2:8" = xmode or
+    # xmode:push CTAs per peer), same steps, max over ranks; each is checked against the default's field moments
     alternatives = None
     if mode == "p2p" and os.environ.get("FB_DIST_COMPARE"):
         alternatives = []
@@ -618,7 +618,7 @@ def run_multi(args, rank, world, local_rank):
             xm, _, he = spec.partition(":")
             plan.dist_set_option("xmode", int(xm))
             if he:
-                plan.dist_set_option("h1_every", int(he))
+                plan.dist_set_option("push_ctas", int(he))
             _, pk_a, sums_a = dr.realise(0, flags, want_pk=True, want_sums=True)
             step(1)
             torch.cuda.synchronize()
@@ -634,10 +634,11 @@ def run_multi(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             same = abs(sums_a[0] - sums0[0]) <= 1e-9 * abs(sums0[1]) ** 0.5 + 1e-9 * abs(sums0[0]) and \
                 abs(sums_a[1] - sums0[1]) <= 1e-10 * abs(sums0[1])
-            alternatives.append({"xmode": int(xm), "h1_every": int(he) if he else None, "ms_per_step": float(tt[0]),
+            alternatives.append({"xmode": int(xm), "push_ctas": int(he) if he else None, "ms_per_step": float(tt[0]),
                                  "field_moments_equal_default": bool(same),
                                  "pk_count_sum_ok": bool(int(pk_a["count"].sum()) == N ** 3)})
         plan.dist_set_option("xmode", base_mode)
+        plan.dist_set_option("push_ctas", int(os.environ.get("FB_DIST_PUSH_CTAS", "0")) or max(4, 32 // max(1, world - 1)))
 
     # result checks on the full-size box itself: every mode binned once, Parseval (box.py:944-946)
     if mode == "p2p":
@@ -706,11 +707,7 @@ def run_multi(args, rank, world, local_rank):
         check = dict(check or {}, count_sum=int(pk["count"].sum()), count_sum_expected=N ** 3,
                      count_sum_ok=bool(int(pk["count"].sum()) == N ** 3), parseval_ratio=parseval)
         xmode = int(os.environ.get("FB_DIST_XMODE", str(DIST_XMODE_DEFAULT)))
-        mech = {4: "the y pass writes per-destination blocks that a high-priority copy kernel (a few CTAs per peer, "
-                   "16-byte peer stores) pushes into the peers' receive buffers while the k-space passes of the next "
-                   "chunk run; the z axis is split in two halves, first halves are sent first and announced by their "
-                   "own epoch flags, so the x pass of the first half of the columns overlaps the rest of the exchange",
-                0: "the y pass stores straight into the peers' receive buffers",
+        mech = {0: "the y pass stores straight into the peers' receive buffers",
                 1: "the y pass writes per-destination blocks that the copy engines push into the peers' receive buffers",
                 2: "the y pass writes per-destination blocks that a high-priority copy kernel (a few CTAs per peer, "
                    "16-byte peer stores) pushes into the peers' receive buffers while the k-space passes of the next "

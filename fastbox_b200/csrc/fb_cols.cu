@@ -104,15 +104,7 @@ static int launch_x_t(fb_plan* p, const XArgs& a, bool inverse) {
         set_error("x pass: ncols=%zu not a multiple of %d", a.ncols, CZ);
         return -1;
     }
-    unsigned grid = (unsigned)(a.ncols / CZ);
-    if (a.zw_cols) {
-        if (!inverse || a.zrow <= 0 || a.ncols % a.zrow || a.zw_cols % CZ || a.zw_off % CZ ||
-            a.zw_off + a.zw_cols > a.zrow) {
-            set_error("x pass: bad z window (%d columns at %d of rows of %d, tiles of %d)", a.zw_cols, a.zw_off, a.zrow, CZ);
-            return -1;
-        }
-        grid = (unsigned)(a.ncols / a.zrow) * (unsigned)(a.zw_cols / CZ);
-    }
+    const unsigned grid = (unsigned)(a.ncols / CZ);
     if (inverse) {
         auto kern = k_x_c2r<N, CZ>;
         if (set_smem(kern, G::SMEM)) return -2;

@@ -59,13 +59,6 @@ struct fb_dist_state {
     cudaEvent_t ev_y[FB_DIST_MAX_CHUNKS], ev_cp[FB_MAX_RANKS];
     cudaStream_t push;              // xmode 2: highest-priority stream of the copy kernel
     int push_ctas;                  // CTAs per peer
-    //   4 = as 2 with the z axis split in two halves: the copy kernel sends the first half of every chunk's rows
-    //       at once and the second halves behind (one second half after every `h1_every` chunks, the rest at the
-    //       end); a second set of epoch flags announces "first halves complete", so the x pass of the first half of
-    //       the columns runs while the second halves are still crossing NVLink.
-    int h1_every;
-    unsigned long long epoch_half;  // epoch counter of the "first z half complete" flags (off_flags + 128)
-    cudaEvent_t ev_pk;
 };
 
 namespace fb {
@@ -91,10 +84,6 @@ struct PushArgs {
     const uint4* src[FB_MAX_RANKS];
     uint4* dst[FB_MAX_RANKS];
     size_t n16;
-    // xmode 4: the n16 elements are rows of 2^row_shift elements, `row_stride16` apart on both sides (a z range of
-    // the [plane][y'][z] blocks); row_shift = 0: one contiguous run
-    int row_shift;
-    size_t row_stride16;
 };
 __global__ void __launch_bounds__(512) k_dist_push(const PushArgs a) {
     const uint4* __restrict__ s = a.src[blockIdx.y];
@@ -102,19 +91,6 @@ __global__ void __launch_bounds__(512) k_dist_push(const PushArgs a) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int UN = 8;
-    if (a.row_shift) {
-        const size_t mask = ((size_t)1 << a.row_shift) - 1;
-        auto off = [&](size_t j) { return (j >> a.row_shift) * a.row_stride16 + (j & mask); };
-        for (; i + (UN - 1) * stride < a.n16; i += UN * stride) {
-            uint4 v[UN];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) v[u] = __ldcs(s + off(i + u * stride));
-#pragma unroll
-            for (int u = 0; u < UN; ++u) d[off(i + u * stride)] = v[u];
-        }
-        for (; i < a.n16; i += stride) d[off(i)] = __ldcs(s + off(i));
-        return;
-    }
     for (; i + (UN - 1) * stride < a.n16; i += UN * stride) {
         uint4 v[UN];
 #pragma unroll
@@ -272,7 +248,6 @@ void dist_destroy(fb_plan* p) {
         if (d->ev_rows[c]) cudaEventDestroy(d->ev_rows[c]);
     if (d->ev_start) cudaEventDestroy(d->ev_start);
     if (d->ev_ydone) cudaEventDestroy(d->ev_ydone);
-    if (d->ev_pk) cudaEventDestroy(d->ev_pk);
     if (d->err_dev) cudaFree(d->err_dev);
     if (d->err_host) cudaFreeHost(d->err_host);
     if (d->send) cudaFree(d->send);
@@ -293,21 +268,6 @@ static PeerBlocks peer_blocks(const fb_dist_state* d) {
     return pb;
 }
 
-// the "first z half complete" flags (xmode 4): raised on the stream of the copy kernel, awaited on the plan stream
-static int dist_signal_half(fb_plan* p, cudaStream_t st) {
-    fb_dist_state* d = p->dist;
-    ++d->epoch_half;
-    k_dist_signal<<<1, 32, 0, st>>>(peer_blocks(d), d->off_flags + 128, d->rank, d->world, d->epoch_half);
-    FB_LAUNCH_CHECK();
-    return 0;
-}
-static int dist_wait_half(fb_plan* p) {
-    fb_dist_state* d = p->dist;
-    k_dist_wait<<<1, 32, 0, p->stream>>>(d->block, d->off_flags + 128, d->world, d->epoch_half,
-                                         (unsigned long long)(d->timeout_s * 1e9), d->err_dev);
-    FB_LAUNCH_CHECK();
-    return 0;
-}
 static int dist_signal(fb_plan* p) {
     fb_dist_state* d = p->dist;
     ++d->epoch;
@@ -398,8 +358,6 @@ int fb_dist_init(fb_plan* p, int rank, int world, int with_forward) {
     for (int c = 0; c < FB_DIST_MAX_CHUNKS; ++c) FB_CUDA(cudaEventCreateWithFlags(&d->ev_rows[c], cudaEventDisableTiming));
     FB_CUDA(cudaEventCreateWithFlags(&d->ev_start, cudaEventDisableTiming));
     FB_CUDA(cudaEventCreateWithFlags(&d->ev_ydone, cudaEventDisableTiming));
-    FB_CUDA(cudaEventCreateWithFlags(&d->ev_pk, cudaEventDisableTiming));
-    d->h1_every = env_int("FB_DIST_H1_EVERY", 2);
     FB_CUDA(cudaMalloc((void**)&d->err_dev, sizeof(int)));
     FB_CUDA(cudaMemset(d->err_dev, 0, sizeof(int)));
     FB_CUDA(cudaMallocHost((void**)&d->err_host, sizeof(int)));
@@ -532,25 +490,6 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
         memset(&vout, 0, sizeof(vout));
         vout.ny = ny;
         while ((1 << vout.ny_shift) < ny) ++vout.ny_shift;
-        // xmode 4: half h (z in [h N/2, (h+1) N/2)) of the rows of chunk cc, to every peer
-        int h1_done = 0;
-        auto push_half = [&](int cc, int h) -> int {
-            const int q0 = cc * nc, nq = (cc == chunks - 1) ? na - q0 : nc;
-            const float2* sc = d->send + (size_t)q0 * N * N;
-            const size_t blk = (size_t)nq * ny * N, half = (size_t)N / 2;
-            PushArgs pa;
-            memset(&pa, 0, sizeof(pa));
-            pa.n16 = (size_t)nq * ny * half * sizeof(float2) / sizeof(uint4);
-            while (((size_t)1 << pa.row_shift) < half * sizeof(float2) / sizeof(uint4)) ++pa.row_shift;
-            pa.row_stride16 = (size_t)N * sizeof(float2) / sizeof(uint4);
-            for (int k = 0; k < d->world - 1; ++k) {
-                const int r = (d->rank + 1 + k) % d->world;
-                pa.src[k] = reinterpret_cast<const uint4*>(sc + (size_t)r * blk + h * half);
-                pa.dst[k] = reinterpret_cast<uint4*>(reinterpret_cast<float2*>(d->peer[r] + d->off_recv[buf]) +
-                                                     (size_t)(p->a0 + q0) * ny * N + h * half);
-            }
-            return launch_push(p, d, pa, d->push);
-        };
         for (int c = 0; c < chunks; ++c) {
             const int pl0 = c * nc, npl = (c == chunks - 1) ? na - pl0 : nc;
             RowsArgs ra;
@@ -585,12 +524,7 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                     reinterpret_cast<float2*>(d->block + d->off_recv[buf]) + (size_t)(p->a0 + pl0) * ny * N;
                 if (launch_cols_views(p, plain_view(p->work + (size_t)pl0 * N * N), vsend, npl, +1, p->stream, 0)) return -3;
                 FB_CUDA(cudaEventRecord(d->ev_y[c], p->stream));
-                if (d->world > 1 && d->xmode == 4) {
-                    FB_CUDA(cudaStreamWaitEvent(d->push, d->ev_y[c], 0));
-                    if (push_half(c, 0)) return -3;
-                    if ((c + 1) % d->h1_every == 0 && h1_done < c + 1)
-                        if (push_half(h1_done++, 1)) return -3;
-                } else if (d->world > 1) {
+                if (d->world > 1) {
                     const size_t blk = (size_t)npl * ny * N;
                     PushArgs pa;
                     memset(&pa, 0, sizeof(pa));
@@ -626,7 +560,7 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                 FB_CUDA(cudaEventRecord(d->ev_cp[r], d->cps[r]));
                 FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[r], 0));
             }
-        } else if (d->xmode >= 2 && d->xmode != 4) {
+        } else if (d->xmode >= 2) {
             FB_CUDA(cudaEventRecord(d->ev_cp[0], d->push));
             FB_CUDA(cudaStreamWaitEvent(p->stream, d->ev_cp[0], 0));
         }
@@ -636,29 +570,13 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
                                                             d->pkx_slot, d->rank, d->world);
             FB_LAUNCH_CHECK();
         }
-        if (d->xmode == 4) {
-            // The plan stream does not wait for the copy kernel: on its stream, behind the first halves of all
-            // chunks, come the "first half complete" flags, the remaining second halves and -- once the shared P(k)
-            // moments are out -- the barrier flags.  The x pass of phase 2 starts on the first flags.
-            FB_CUDA(cudaEventRecord(d->ev_pk, p->stream));
-            if (dist_signal_half(p, d->push)) return -3;
-            if (d->world > 1)
-                while (h1_done < chunks)
-                    if (push_half(h1_done++, 1)) return -3;
-            FB_CUDA(cudaStreamWaitEvent(d->push, d->ev_pk, 0));
-            {
-                StreamScope sc(p, d->push);
-                if (dist_signal(p)) return -3;
-            }
-        } else if (dist_signal(p)) {
-            return -3;
-        }
+        if (dist_signal(p)) return -3;
         cudaEventRecord(p->ev[1], p->stream);
     }
     if (phase != 1) {
         FB_CHECK(field_out != nullptr && is_device_ptr(field_out), "fb_dist_realise: field_out must be device memory");
         const int buf = (int)(d->inv_step & 1);
-        if (d->xmode == 4 ? dist_wait_half(p) : dist_wait(p)) return -3;
+        if (dist_wait(p)) return -3;
         cudaEventRecord(p->ev[2], p->stream);
         XArgs xa;
         memset(&xa, 0, sizeof(xa));
@@ -670,15 +588,6 @@ int fb_dist_realise(fb_plan* p, uint64_t seed, int flags, float scale, int chunk
         xa.scale = (float)((double)scale / ((double)N * N * N));
         xa.sums = sums_out ? p->scal : nullptr;
         if (sums_out && scal_clear(p)) return -2;
-        if (d->xmode == 4) {
-            if ((N / 2) % 64 == 0) {                         // the window must hold whole x-pass tiles (<= 32 columns)
-                xa.zrow = N;
-                xa.zw_cols = N / 2;
-                if (launch_x_c2r(p, xa)) return -3;          // columns of the first z half: all their planes are in
-                xa.zw_off = N / 2;
-            }
-            if (dist_wait(p)) return -3;
-        }
         if (launch_x_c2r(p, xa)) return -3;
         cudaEventRecord(p->ev[3], p->stream);
         p->n_last = 3;
@@ -706,11 +615,8 @@ int fb_dist_set_option(fb_plan* p, const char* key, int value) {
         FB_CHECK(value >= 1 && value <= 64, "push_ctas must be in 1..64");
         d->push_ctas = value;
     } else if (!strcmp(key, "xmode")) {
-        FB_CHECK(value >= 0 && value <= 4, "xmode must be 0..4");
+        FB_CHECK(value >= 0 && value <= 3, "xmode must be 0..3");
         d->xmode = value;
-    } else if (!strcmp(key, "h1_every")) {
-        FB_CHECK(value >= 1, "h1_every must be >= 1");
-        d->h1_every = value;
     } else if (!strcmp(key, "cz_cols")) {
         d->cz_cols = value;
     } else {

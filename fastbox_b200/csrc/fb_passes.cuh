@@ -879,18 +879,7 @@ struct XArgs {
     // NVLink); nranks = 0: everything goes to spec_out
     float2* peer_out[FB_MAX_RANKS];
     int nranks, per_shift;
-    // optional window of the z axis (slab-decomposed inverse, fb_dist.cu: the x pass of one z range runs while the
-    // rest of the exchange is still in flight): only columns g = row * zrow + zw_off + [0, zw_cols) are transformed;
-    // zw_cols = 0: all ncols columns
-    int zw_cols, zw_off, zrow;
 };
-template <int CZ>
-__device__ __forceinline__ size_t x_first_col(const XArgs& A) {
-    if (A.zw_cols == 0) return (size_t)blockIdx.x * CZ;
-    const unsigned tpr = (unsigned)A.zw_cols / CZ;                  // tiles per row of the window
-    const unsigned row = blockIdx.x / tpr, tz = blockIdx.x - row * tpr;
-    return (size_t)row * A.zrow + A.zw_off + (size_t)tz * CZ;
-}
 
 template <int N, int CZ>
 struct XGeom {
@@ -910,7 +899,7 @@ __global__ void __launch_bounds__(XGeom<N, CZ>::THREADS, XGeom<N, CZ>::MINB) k_x
     float2* sm = reinterpret_cast<float2*>(smem_raw);
     __shared__ double red[2][32];
     const int col = threadIdx.x % CZ, t = threadIdx.x / CZ;
-    const size_t g = x_first_col<CZ>(A) + col;
+    const size_t g = (size_t)blockIdx.x * CZ + col;
     const float2* src = A.spec + g;
     ColLayout<CZ> sl{col};
     float2 v[P];

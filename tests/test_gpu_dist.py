@@ -133,14 +133,12 @@ def _nvlink_tables(plan, N, L, edges, filt=None):
 @pytest.mark.parametrize("N,world,chunks,xmode", [(32, 1, 1, 0), (64, 1, 4, 0), (32, 2, 1, 0), (64, 2, 2, 0),
                                                   (64, 4, 2, 0), (128, 8, 2, 0), (64, 2, 2, 1), (128, 8, 4, 1),
                                                   (64, 2, 2, 2), (128, 8, 4, 2), (64, 4, 1, 2), (64, 2, 2, 3), (128, 8, 4, 3),
-                                                  (256, 2, 4, 3), (32, 1, 2, 4), (64, 2, 2, 4), (64, 4, 1, 4),
-                                                  (128, 8, 4, 4), (256, 2, 16, 4), (128, 4, 16, 4)])
+                                                  (256, 2, 4, 3)])
 def test_library_exchange_emulated_ranks(gpu, monkeypatch, N, world, chunks, xmode):
     """
     fb_dist_realise / fb_dist_power_spectrum: `world` plans on one GPU, connected through their handles.
     xmode 0: the y pass stores into the peers' buffers; 1: local blocks + copy-engine transfers; 2: local blocks +
-    the high-priority copy kernel; 3: the copy kernel drives the bulk copy engine (cp.async.bulk); 4: as 2 with the z
-    axis in two halves (first halves first, own flags, x pass per half).
+    the high-priority copy kernel; 3: the copy kernel drives the bulk copy engine (cp.async.bulk).
     """
     monkeypatch.setenv("FB_DIST_XMODE", str(xmode))
     L = (1e3, 1e3, 1e3)
