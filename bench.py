@@ -613,12 +613,12 @@ def run_multi(args, rank, world, local_rank):
     if mode == "p2p" and os.environ.get("FB_DIST_COMPARE"):
         alternatives = []
         base_mode = int(os.environ.get("FB_DIST_XMODE", str(DIST_XMODE_DEFAULT)))
+        default_push_ctas = int(os.environ.get("FB_DIST_PUSH_CTAS", "0")) or max(4, 32 // max(1, world - 1))
         _, _, sums0 = dr.realise(0, flags, want_pk=True, want_sums=True)
         for spec in os.environ["FB_DIST_COMPARE"].split(","):
             xm, _, he = spec.partition(":")
             plan.dist_set_option("xmode", int(xm))
-            if he:
-                plan.dist_set_option("push_ctas", int(he))
+            plan.dist_set_option("push_ctas", int(he) if he else default_push_ctas)
             _, pk_a, sums_a = dr.realise(0, flags, want_pk=True, want_sums=True)
             step(1)
             torch.cuda.synchronize()
@@ -638,7 +638,7 @@ def run_multi(args, rank, world, local_rank):
                                  "field_moments_equal_default": bool(same),
                                  "pk_count_sum_ok": bool(int(pk_a["count"].sum()) == N ** 3)})
         plan.dist_set_option("xmode", base_mode)
-        plan.dist_set_option("push_ctas", int(os.environ.get("FB_DIST_PUSH_CTAS", "0")) or max(4, 32 // max(1, world - 1)))
+        plan.dist_set_option("push_ctas", default_push_ctas)
 
     # result checks on the full-size box itself: every mode binned once, Parseval (box.py:944-946)
     if mode == "p2p":
