@@ -121,3 +121,52 @@ def test_shim_two_point_statistics(gpu):
     assert np.all(np.abs(xerr - werr) <= 10 * TOL * werr + 1e-9 * np.abs(want).max())
     with pytest.raises(ValueError):
         box.binned_power_spectrum_2d(delta_x=box.delta_x, delta_k=box.delta_k)
+
+
+def test_device_multipoles_kaiser_and_cross_at_256(gpu):
+    """
+    Multipoles and cross power are unpinned w.r.t. nbodykit (absent), so the DEVICE path is tied to known answers as
+    well: a field with spectrum (1 + beta mu^2) d(k), |d|^2 = boxfactor, must give the Kaiser / Hamilton multipoles
+    P_0 = 1 + 2 beta/3 + beta^2/5, P_2 = 4 beta/3 + 4 beta^2/7, P_4 = 8 beta^2/35 (to the quadrature error of the
+    discrete shells, which falls as 1/N^2), and the NumPy restatement to the usual tolerance; cross(a, c a) = c auto(a).
+    """
+    N, L = 256, (5e2, 5e2, 5e2)
+    rng = np.random.default_rng(5)
+    half = R.rfft3_axis0(rng.standard_normal((N, N, N)))
+    half = half / np.maximum(np.abs(half), 1e-300) * np.sqrt(R.boxfactor(N, *L))
+    m = R.mode_numbers(N).astype(np.float64)
+    h = N // 2 + 1
+    kk = np.sqrt(m[:h, None, None] ** 2 + m[None, :, None] ** 2 + m[None, None, :] ** 2)
+    with np.errstate(all="ignore"):
+        mu = np.where(kk > 0, m[None, None, :] / kk, 0.0)
+    del kk
+    beta = 0.6
+    half_s = half * (1.0 + beta * mu ** 2)
+    del mu
+    # a real field needs real self-conjugate modes; the planes a = 0 and a = N/2 are made Hermitian by the
+    # transform pair itself (c2r drops the inconsistent parts), so measure what the device sees: go through the field
+    field = R.irfft3_axis0(half_s).astype(np.float32)
+    half_seen = R.rfft3_axis0(field.astype(np.float64))
+    knyq = np.pi * N / L[0]
+    edges = np.concatenate([[0.0], np.linspace(0.3 * knyq, 0.98 * knyq, 5)])
+    plan = setup_plan(N, L, 0.0, nbins=20)[0]
+    plan.set_pk_bins(ks.bin_thresholds(edges))
+    res = plan.field_to_spectrum(field, want_pk=True, poles=True)
+    cnt = res["count"][:edges.size].astype(np.float64)
+    p0 = (res["sum1"][:edges.size] / cnt)[2:]                   # bins between the four upper edges
+    p2 = (5.0 * res["sum_l2"][:edges.size] / cnt)[2:]
+    p4 = (9.0 * res["sum_l4"][:edges.size] / cnt)[2:]
+    _, poles = R.pk_multipoles(half_seen, N, *L, kbins=edges)
+    for got, ell in ((p0, 0), (p2, 2), (p4, 4)):
+        assert np.all(np.abs(got - poles[ell][1:]) <= 20 * TOL * np.abs(poles[0][1:])), ell
+    want = {0: 1 + 2 * beta / 3 + beta ** 2 / 5, 2: 4 * beta / 3 + 4 * beta ** 2 / 7, 4: 8 * beta ** 2 / 35}
+    for got, ell, tol in ((p0, 0, 2e-3), (p2, 2, 4e-3), (p4, 4, 8e-3)):
+        assert np.all(np.abs(got - want[ell]) < tol), (ell, got, want[ell])
+    # cross power of the field with 2.5 x itself = 2.5 x its auto power, bin by bin (and the same populations)
+    spec_b = plan.alloc((N // 2 + 1) * N * N * 8)
+    plan.field_to_spectrum((2.5 * field).astype(np.float32), spec_out=spec_b)
+    resx = plan.field_to_spectrum(field, cross=spec_b, want_pk=True)
+    assert np.array_equal(resx["count"], res["count"])
+    ok = res["count"][:edges.size] > 0
+    assert np.allclose(resx["sum1"][:edges.size][ok], 2.5 * res["sum1"][:edges.size][ok], rtol=1e-6)
+    plan.close()
