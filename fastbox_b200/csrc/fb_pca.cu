@@ -7,10 +7,10 @@
 // ~1e-2 of the signal, and an error eps in the covariance leaks a foreground mode as eps*lambda_1/sqrt(lambda_i).
 // The cube is [pixel][channel] (channel contiguous), exactly field.reshape(-1, Nf) of the reference.
 //
-// k_pca_cov: tall-skinny X^T X.  A CTA owns one 64 x 64 tile of the upper triangle and one slice of the
-// pixels; 256 threads hold 4 x 4 float64 accumulators each; panels of 16 pixels x 64 channels go through
-// shared memory (mean subtracted on the way in); partial tiles are added to the global matrix with float64
-// reductions.  FP64-FMA bound: 2 * Nf^2/2 * Npix flops.
+// Covariance = tall-skinny X^T X, 2 * Nf^2/2 * Npix flops: k_pca_cov_mma (from 256 channels on: 128 x 128 tiles of the
+// upper triangle x pixel slices on the FP64 tensor path, see there) and k_pca_cov (fewer or an odd number of channels:
+// 64 x 64 tiles, 256 threads with 4 x 4 float64 accumulators each, panels of 16 pixels x 64 channels through shared
+// memory, mean subtracted on the way in); partial tiles are added to the global matrix with float64 reductions.
 // k_pca_project_warp: one warp per line of sight, row in registers, operator in shared memory (nmodes <= 8);
 // k_pca_project: general fallback, one CTA per line of sight with block reductions.
 #include "fb_launch.h"
@@ -18,6 +18,7 @@
 namespace fb {
 
 constexpr int PCA_TILE = 64, PCA_KT = 16;
+
 
 __global__ void __launch_bounds__(256) k_pca_sums(const double* __restrict__ x, int nf, size_t npix,
                                                    double* __restrict__ sums) {
@@ -102,42 +103,56 @@ __global__ void __launch_bounds__(256) k_pca_cov(const double* __restrict__ x, c
         }
 }
 
-// k_pca_cov128: the same contraction on 128 x 128 tiles with 8 x 8 float64 accumulators per thread.
-// The 4 x 4 kernel above reads 8 shared-memory words for 16 FMAs, which keeps the shared-memory pipe exactly as
-// busy as the FP64 pipe (64 wavefronts against 64 FMA cycles per k and CTA), and its panels are loaded, stored
-// and consumed in sequence.  Here a thread reads its 8 + 8 operands as eight 16-byte loads for 64 FMAs (lanes of
-// a warp form an 8 x 4 patch, so one load instruction touches at most 128 contiguous bytes: 8 wavefronts for 2048
-// FMAs), the next panel of KT pixels is fetched into registers while the current one is consumed (one barrier per
-// panel, two shared-memory buffers), and the cube goes through L2 nine times instead of seventeen.  Output element
-// (i, j) of a thread: f = f0 + 2 ty + (i & 1) + 32 (i >> 1), g = g0 + 2 tx + (j & 1) + 32 (j >> 1).  Diagonal
-// tiles skip their lower-left 64 x 64 quadrant (never read by k_pca_cov_finish).  nf must be even (16-byte loads).
+// D(8 x 8) += A(8 x 4) B(4 x 8) on the FP64 tensor path.  tcgen05 has no float64 kind, so mma.sync m8n8k4 is the only
+// tensor-core route for this contraction.  Lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and D[l >> 2][2 (l & 3) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// k_pca_cov_mma: X^T X on 128 x 128 tiles of the upper triangle x pixel slices, on the FP64 tensor path (used from
+// 256 channels on).  Eight warps in a 2 (f) x 4 (g) grid own 64 x 32 outputs each = 8 x 4 MMA tiles (64 accumulator
+// registers per lane); per group of four pixels a warp reads 8 + 4 operand fragments (one float64 per lane each) for
+// 32 MMAs = 8192 FMAs.  A fragment A[f][p] = X[p][f] is the element (pixel 4 kg + (l & 3), channel f0 + (l >> 2)) of
+// the panel, B the same of the g panel: rows are padded to 136 float64 so that the four pixel rows of a fragment
+// fall on the two halves of the banks (a 256-byte warp request in its minimum of two wavefronts).
+// Panels of KT pixels x 128 channels are double buffered in shared memory; the next panel is fetched into registers
+// while the current one is consumed and its channel means are subtracted only when it is parked, so that nothing
+// ahead of the MMA block waits on a load in flight (an earlier build subtracted right after the loads: every warp then
+// stalled on its prefetch first, 75 ms instead of 50); one barrier per panel; the grid is nine whole waves of one CTA
+// per SM; diagonal tiles skip their lower-left 64 x 64 quadrant (never read by k_pca_cov_finish).  nf must be even
+// (16-byte loads).  History (profiles/README.md): the same tile with 8 x 8 SIMT accumulators per thread read four
+// times the shared-memory words per FMA and kept that pipe about as busy as the FP64 pipe:
+// 50.5 ms at 1024^3 against 43.3 ms here; the 64 x 64 kernel above: 77 ms.
 template <int KT>
-__global__ void __launch_bounds__(256, 1) k_pca_cov128(const double* __restrict__ x, const double* __restrict__ mean,
-                                                        int nf, size_t npix, int ntile, double* __restrict__ cov) {
-    constexpr int TL = 128;
-    constexpr int RPT = KT / 4;                                      // panel rows per loader thread
+__global__ void __launch_bounds__(256, 1) k_pca_cov_mma(const double* __restrict__ x, const double* __restrict__ mean,
+                                                         int nf, size_t npix, int ntile, double* __restrict__ cov) {
+    constexpr int TL = 128, LD = 136;
+    constexpr int RPT = KT / 4;
     extern __shared__ __align__(16) unsigned char pca_cov_smem[];
-    double (*sa)[KT][TL] = reinterpret_cast<double (*)[KT][TL]>(pca_cov_smem);                 // [2][KT][TL]
-    double (*sb)[KT][TL] = reinterpret_cast<double (*)[KT][TL]>(pca_cov_smem + 2 * sizeof(double) * KT * TL);
+    double (*sa)[KT][LD] = reinterpret_cast<double (*)[KT][LD]>(pca_cov_smem);                 // [2][KT][LD]
+    double (*sb)[KT][LD] = reinterpret_cast<double (*)[KT][LD]>(pca_cov_smem + 2 * sizeof(double) * KT * LD);
     int ti = 0, rem = blockIdx.x;
     while (rem >= ntile - ti) {
         rem -= ntile - ti;
         ++ti;
     }
     const int tj = ti + rem;
-    const bool diag = ti == tj;
     const int f0 = ti * TL, g0 = tj * TL;
     const size_t per_slice = ((npix + gridDim.y - 1) / gridDim.y + KT - 1) / KT * KT;
     const size_t p0 = (size_t)blockIdx.y * per_slice;
     const size_t p1 = p0 + per_slice < npix ? p0 + per_slice : npix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx = (lane & 7) + 8 * (warp & 1), ty = (lane >> 3) + 4 * (warp >> 1);   // 16 x 16 threads
-    const int lc = 2 * (threadIdx.x & 63), lr = threadIdx.x >> 6;                     // loader: channel pair, row 0..3
-    double acc[8][8];
+    const int wf = warp & 1, wg = warp >> 1;                         // warp tile: f in [64 wf, +64), g in [32 wg, +32)
+    const int fr = lane >> 2, kc = lane & 3;
+    const bool active = !(ti == tj && wf == 1 && wg < 2);            // lower-left quadrant of a diagonal tile
+    const int lc = 2 * (threadIdx.x & 63), lr = threadIdx.x >> 6;    // loader: channel pair, row 0..3
+    double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const bool oka = f0 + lc < nf, okb = g0 + lc < nf;
     double2 ma = make_double2(0.0, 0.0), mb = ma;
     if (oka) ma = *reinterpret_cast<const double2*>(mean + f0 + lc);
@@ -151,14 +166,12 @@ __global__ void __launch_bounds__(256, 1) k_pca_cov128(const double* __restrict_
             rb[r] = mb;
             if (p < p1) {
                 const double* row = x + p * (size_t)nf;
-                // raw values: the mean is subtracted in park(), after the panel in between has been consumed, so that
-                // nothing waits on these loads before the FMA block (out-of-range lanes hold the mean itself -> 0)
                 if (oka) ra[r] = __ldg(reinterpret_cast<const double2*>(row + f0 + lc));
                 if (okb) rb[r] = __ldg(reinterpret_cast<const double2*>(row + g0 + lc));
             }
         }
     };
-    auto park = [&](int b) {
+    auto park = [&](int b) {                                         // means subtracted here, not in fetch()
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             *reinterpret_cast<double2*>(&sa[b][lr + 4 * r][lc]) = make_double2(ra[r].x - ma.x, ra[r].y - ma.y);
@@ -173,43 +186,37 @@ __global__ void __launch_bounds__(256, 1) k_pca_cov128(const double* __restrict_
     int cur = 0;
     for (size_t pb = p0; pb < p1; pb += KT, cur ^= 1) {
         const bool more = pb + KT < p1;
-        if (more) fetch(pb + KT);                                   // in flight while this panel is consumed
+        if (more) fetch(pb + KT);
+        if (active) {
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            double a[8], b[8];
+            for (int kg = 0; kg < KT / 4; ++kg) {
+                const double* pa = &sa[cur][4 * kg + kc][64 * wf + fr];
+                const double* pb2 = &sb[cur][4 * kg + kc][32 * wg + fr];
+                double a[8], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double2 va = *reinterpret_cast<const double2*>(&sa[cur][k][2 * ty + 32 * i]);
-                const double2 vb = *reinterpret_cast<const double2*>(&sb[cur][k][2 * tx + 32 * i]);
-                a[2 * i] = va.x;
-                a[2 * i + 1] = va.y;
-                b[2 * i] = vb.x;
-                b[2 * i + 1] = vb.y;
+                for (int i = 0; i < 8; ++i) a[i] = pa[8 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = pb2[8 * j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (!(diag && i >= 4 && j < 4)) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         if (more) park(cur ^ 1);
         __syncthreads();
     }
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int f = f0 + 2 * ty + (i & 1) + 32 * (i >> 1), g = g0 + 2 * tx + (j & 1) + 32 * (j >> 1);
-            if (f < nf && g < nf && !(diag && i >= 4 && j < 4)) atomicAdd(&cov[(size_t)f * nf + g], acc[i][j]);
-        }
-}
-
-// (An FP64 tensor-core variant of this kernel -- mma.sync m8n8k4 on the same tiles -- was measured at 99 ms against
-// 88 ms for the SIMT kernel at 1024^3 and removed: the limit is not the FP64 pipe, see profiles/README.md.)
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {      // fb_bench_fp64 probe
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int f = f0 + 64 * wf + 8 * i + fr, g = g0 + 32 * wg + 8 * j + 2 * kc + v;
+                    if (f < nf && g < nf) atomicAdd(&cov[(size_t)f * nf + g], acc[i][j][v]);
+                }
+    }
 }
 
 // mirror the upper-triangle tiles into the lower triangle and apply the 1/(npix-1) of np.cov
@@ -379,7 +386,8 @@ int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* 
         FB_LAUNCH_CHECK();
     }
     FB_CUDA(cudaMemsetAsync(d_cov, 0, (size_t)nf * nf * sizeof(double), p->stream));
-    // 128 x 128 tiles (k_pca_cov128) from 256 channels on; FB_PCA_TILE=64 keeps the 64 x 64 kernel, FB_PCA_KT the panel depth
+    // 128 x 128 tiles on the FP64 tensor path (k_pca_cov_mma) from 256 channels on; FB_PCA_TILE=64 keeps the 64 x 64 SIMT
+    // kernel, FB_PCA_KT sets the panel depth
     const int tile_opt = env_int("FB_PCA_TILE", nf >= 256 && nf % 2 == 0 ? 128 : 64);
     if (tile_opt == 128 && nf % 2 == 0) {
         const int kt = env_int("FB_PCA_KT", 16);
@@ -392,13 +400,13 @@ int fb_pca_covariance(fb_plan* p, const double* cube, double* mean_out, double* 
         const size_t max_slices = (npix + 4 * kt - 1) / (4 * kt);
         if ((size_t)slices > max_slices) slices = (int)max_slices;
         if (slices < 1) slices = 1;
-        const size_t smem = 4 * sizeof(double) * kt * 128;
+        const size_t smem = 4 * sizeof(double) * kt * 136;
         if (kt == 8) {
-            auto kern = k_pca_cov128<8>;
+            auto kern = k_pca_cov_mma<8>;
             if (set_smem(kern, smem)) return -2;
             kern<<<dim3(ntri, slices), 256, smem, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
         } else {
-            auto kern = k_pca_cov128<16>;
+            auto kern = k_pca_cov_mma<16>;
             if (set_smem(kern, smem)) return -2;
             kern<<<dim3(ntri, slices), 256, smem, p->stream>>>(cube, d_mean, nf, npix, ntile, d_cov);
         }
