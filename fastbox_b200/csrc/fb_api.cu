@@ -50,6 +50,15 @@ int stage_in(fb_plan* p, int slot, const void* ptr, size_t bytes, const void** d
     }
     if (ensure_slot(p, slot, bytes)) return -2;
     FB_CUDA(cudaMemcpyAsync(p->stage[slot], ptr, bytes, cudaMemcpyHostToDevice, p->stream));
+    // The caller owns its buffer again when the call returns.  A copy from pageable memory has left the buffer by
+    // now; one from pinned memory is truly asynchronous and an entry point whose outputs all stay on the device
+    // would return with it in flight, so wait for it here (the kernels that follow depend on it anyway).
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+    } else if (at.type == cudaMemoryTypeHost) {
+        FB_CUDA(cudaStreamSynchronize(p->stream));
+    }
     *dev = p->stage[slot];
     return 0;
 }
@@ -231,6 +240,8 @@ const char* fb_last_error(void) { return fb::g_err; }
 const char* fb_version(void) { return "fastbox_b200 0.1 (sm_100a)"; }
 uint64_t fb_launch_count(void) { return fb::g_launches.load(); }
 
+static int plan_init(fb_plan* p, int N, double Lx, double Ly, double Lz, int device);
+
 int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int device) {
     FB_CHECK(out != nullptr, "fb_plan_create: null output pointer");
     FB_CHECK(N >= 8 && N <= 2048 && (N & (N - 1)) == 0, "fb_plan_create: N=%d must be a power of two in [8,2048]", N);
@@ -246,6 +257,16 @@ int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int de
     FB_CUDA(cudaSetDevice(device));
     fb_plan* p = (fb_plan*)calloc(1, sizeof(fb_plan));
     FB_CHECK(p != nullptr, "out of host memory");
+    const int rc = plan_init(p, N, Lx, Ly, Lz, device);
+    if (rc) {                                            // nothing of a half-built plan is left behind
+        fb_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+
+static int plan_init(fb_plan* p, int N, double Lx, double Ly, double Lz, int device) {
     p->N = N;
     p->Lx = Lx;
     p->Ly = Ly;
@@ -294,14 +315,13 @@ int fb_plan_create(fb_plan** out, int N, double Lx, double Ly, double Lz, int de
     FB_CUDA(cudaMalloc((void**)&p->scal, 8 * sizeof(double)));
     FB_CUDA(cudaMallocHost((void**)&p->scal_host, 8 * sizeof(double)));
     for (int i = 0; i < 8; ++i) FB_CUDA(cudaEventCreate(&p->ev[i]));
-    *out = p;
     return 0;
 }
 
 int fb_plan_destroy(fb_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
-    cudaStreamSynchronize(p->stream);
+    if (p->stream) cudaStreamSynchronize(p->stream);
     fb::dist_destroy(p);
     cudaFree(p->tw);
     cudaFree(p->ax);
@@ -321,8 +341,10 @@ int fb_plan_destroy(fb_plan* p) {
     cudaFree(p->aux);
     cudaFree(p->beam_spec);
     for (int i = 0; i < 6; ++i) cudaFree(p->stage[i]);
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(p->ev[i]);
-    cudaStreamDestroy(p->stream);
+    for (int i = 0; i < 8; ++i)
+        if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    cudaGetLastError();
     free(p);
     return 0;
 }
