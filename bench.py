@@ -169,8 +169,10 @@ def run_reference(args, rank):
     sample = cpu_sample_text(n_ref)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "realise+filter+P(k), %d^3 (bounded sample of the 1024^3 workload)" % n_ref,
+            "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "realise+filter+P(k), %d^3 (bounded sample of the %d^3 workload of the %d-GPU line; "
+                                   "the CPU path is one process on the host cores whatever N is)"
+                                   % (n_ref, args.size if args.gpus == 1 else args.size_multi, args.gpus),
                        "nbins": NBINS},
             "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
