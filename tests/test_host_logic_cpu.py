@@ -214,3 +214,27 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/", "oracle/") or "import oracle" not in txt
                 assert "from oracle" not in txt and "import oracle" not in txt
+
+
+def test_bin_thresholds_property_random_edges_and_boxes():
+    """Property test (hypothesis): for arbitrary increasing edges and box lengths, the sqrt-free threshold search
+    gives np.digitize's index for every mode of a small grid and for values placed on and next to every edge."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.floats(min_value=1e-4, max_value=50.0, allow_nan=False), min_size=2, max_size=24, unique=True),
+           st.tuples(st.floats(10.0, 5e3), st.floats(10.0, 5e3), st.floats(10.0, 5e3)), st.booleans())
+    def check(edges, L, with_zero):
+        edges = np.sort(np.array(edges))
+        if with_zero:
+            edges = np.concatenate([[0.0], edges])
+        thr = ks.bin_thresholds(edges)
+        N = 8
+        s = (ks.axis_sq(N, L[0])[:, None, None] + ks.axis_sq(N, L[1])[None, :, None]) + ks.axis_sq(N, L[2])[None, None, :]
+        k = 2. * np.pi * np.sqrt(s)
+        assert np.array_equal(np.searchsorted(thr, s.ravel(), side="right"), np.digitize(k.ravel(), edges))
+        # values whose k lands exactly on an edge, one ulp below and one above
+        se = (edges / (2. * np.pi)) ** 2
+        for cand in (se, np.nextafter(se, 0.0), np.nextafter(se, np.inf)):
+            assert np.array_equal(np.searchsorted(thr, cand, side="right"), np.digitize(ks.k_of_s(cand), edges))
+    check()
